@@ -1,0 +1,166 @@
+/*
+ * tde_jet.h -- C ABI of the B200-native Taylor-mode jet engine for torch_DE's PINN residual hot path.
+ *
+ * Drop-in boundary.  Each entry point replaces a piece of the reference's
+ * pure-Python/torch.func path; the reference-side binding is the `engine` subclass shown in
+ * INTEGRATION.md (ctypes, `tensor.data_ptr()`, `torch.cuda.current_stream().cuda_stream`).
+ *
+ *   tde_jet_forward    replaces  AD_engine.autodiff + assign_derivs
+ *                                (src/torch_DE/continuous/Engines/AD.py:70-90, 115-131):
+ *                                vmap(jacrev(jacrev(net)))(x) and the per-name slicing.
+ *   tde_jet_backward   replaces  torch autograd's walk of that graph in `loss.backward()`
+ *                                (call sites Tutorials/Spring.py:54, Lid_Driven_Cavity.py:95).
+ *   tde_residual_loss  replaces  Loss_handler.calculate + Loss.{point_error,weighted_point_error,aggregated_loss}
+ *                                (src/torch_DE/utils/loss.py:187-206, 33-59) for residuals expressible as a
+ *                                register program, and emits d(loss)/d(stream) seeds for tde_jet_backward.
+ *   tde_adam_step      replaces  torch.optim.Adam.step on the flat parameter/gradient buffers
+ *                                (Tutorials/Lid_Driven_Cavity.py:71,97) -- same update rule, one launch.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (torch's caching allocator),
+ * all tensors FP32, kernels are enqueued on `stream` and never synchronise the host.  Return value
+ * 0 = ok, non-zero = error (message via tde_last_error()).  No CPU fallback exists.
+ *
+ * Jet channels: channel 0 is the value; channels 1..n_first are d/dx_{first_in[i]}; the remaining
+ * n_second channels are d2/(dx_a dx_b) where a,b index FIRST-ORDER CHANNELS (0-based, a<=b) and the
+ * pairs are sorted by (a,b).  J = 1 + n_first + n_second.
+ */
+#ifndef TDE_JET_H
+#define TDE_JET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDE_ACT_NONE 0
+#define TDE_ACT_TANH 1
+#define TDE_ACT_SIN 2
+
+#define TDE_MAX_LAYERS 24
+#define TDE_MAX_IN 8
+#define TDE_MAX_OUT 4
+#define TDE_MAX_FIRST 3
+#define TDE_MAX_SECOND 6
+
+/* One nn.Linear: weight[out][in] row-major, bias[out] (may be NULL), followed by activation `act`. */
+typedef struct TdeLayer {
+    const float* weight;
+    const float* bias;
+    int32_t in_features;
+    int32_t out_features;
+    int32_t act;
+    int32_t reserved;
+} TdeLayer;
+
+/* MLP.forward (Networks.py:148-152): layers[0..n_layers-2] activated, layers[n_layers-1] is linear_out. */
+typedef struct TdeNet {
+    int32_t n_layers;
+    int32_t reserved;
+    TdeLayer layers[TDE_MAX_LAYERS];
+} TdeNet;
+
+typedef struct TdeJetSpec {
+    int32_t d_in;
+    int32_t n_out;
+    int32_t n_first;
+    int32_t n_second;
+    int32_t first_in[TDE_MAX_FIRST];   /* input column of each first-order channel */
+    int32_t second_a[TDE_MAX_SECOND];  /* first-order channel numbers, a <= b, sorted */
+    int32_t second_b[TDE_MAX_SECOND];
+} TdeJetSpec;
+
+/* Geometry the host needs to size its buffers; filled by tde_plan(). */
+typedef struct TdePlan {
+    int32_t n_channels;       /* J */
+    int32_t width_padded;     /* hidden width rounded up for the kernels */
+    int32_t tile_points;      /* collocation points per CTA tile */
+    int32_t n_ctas;           /* persistent grid size */
+    int64_t n_tiles;
+    int64_t stash_bytes;      /* forward -> backward activation stash (0 if B == 0) */
+    int64_t workspace_bytes;  /* packed weights + per-CTA partial gradients */
+    int64_t n_params;         /* floats in the flat gradient, net.parameters() order */
+    int32_t smem_forward;
+    int32_t smem_backward;
+} TdePlan;
+
+const char* tde_last_error(void);
+int tde_version(void);
+
+/* Validates (net, spec) and reports buffer sizes for a batch of n_points. Host-only, no launch. */
+int tde_plan(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points, TdePlan* plan);
+
+/*
+ * Forward jets.  x[n_points][d_in] row-major.  out[(c*n_out + o)*ld_out + p] = channel c of output o at
+ * point p (SoA: one contiguous stream per (channel, output)).  stash may be NULL (inference / value-only
+ * groups: nothing is kept for a backward).  workspace must hold plan.workspace_bytes.
+ */
+int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points,
+                    float* out, int64_t ld_out, float* stash, void* workspace, void* stream);
+
+/*
+ * Reverse sweep.  seeds has the layout of `out` (d loss / d out); flat_grad[n_params] is ACCUMULATED
+ * into (caller zeroes), laid out W0,b0,W1,b1,...,Wout,bout exactly like net.parameters().
+ * grad_scale multiplies the contribution (1/N_global for data-parallel means).
+ * May be called repeatedly on one stash (GradNorm: utils/Loss_weighting.py:39, retain_graph=True).
+ */
+int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points,
+                     const float* stash, const float* seeds, int64_t ld_seeds, float grad_scale,
+                     float* flat_grad, void* workspace, void* stream);
+
+/* ---- fused residual assembly + loss reduction ------------------------------------------------ */
+#define TDE_OP_CONST 0  /* dst = imm                      */
+#define TDE_OP_LOAD 1   /* dst = stream[a][p]             (a = row of `streams`)                 */
+#define TDE_OP_AUX 2    /* dst = aux[a][p]                (per-point constants: x, y, sdf, rhs)  */
+#define TDE_OP_ADD 3
+#define TDE_OP_SUB 4
+#define TDE_OP_MUL 5
+#define TDE_OP_NEG 6
+#define TDE_OP_POWI 7   /* dst = src_a ** (int)imm        */
+#define TDE_OP_ABS 8
+#define TDE_OP_SIN 9
+#define TDE_OP_COS 10
+#define TDE_OP_DIV 11
+#define TDE_MAX_REGS 48
+#define TDE_MAX_OPS 96
+#define TDE_MAX_ROWS 8
+
+typedef struct TdeOp {
+    int32_t op, dst, a, b;
+    float imm;
+} TdeOp;
+
+/* One loss-table group: `n_rows` residuals over the same points; row r reads register res_reg[r],
+ * weight is aux row w_aux[r] (or the constant w_const[r] if w_aux[r] < 0); loss_r = coef[r]*mean(w*|res|^2). */
+typedef struct TdeLossProgram {
+    int32_t n_ops;
+    int32_t n_rows;
+    TdeOp ops[TDE_MAX_OPS];
+    int32_t res_reg[TDE_MAX_ROWS];
+    int32_t w_aux[TDE_MAX_ROWS];
+    float w_const[TDE_MAX_ROWS];
+    float coef[TDE_MAX_ROWS];
+} TdeLossProgram;
+
+/*
+ * streams[(row)*ld + p] for p in [p0, p0+n) (row indexing as `out` above), aux[(row)*ld_aux + p - p0].
+ * row_sums[n_rows] += sum_p w*|res|^2 * inv_count   (un-weighted by coef; caller recombines)
+ * seeds[(row)*ld + p] = coef_r * inv_count * d(w*res^2)/d(stream)   (overwrites the [p0,p0+n) slice;
+ * rows never loaded get zeros).  point_res (optional) [n_rows][n]: per-point residuals (R3 sampler).
+ */
+int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
+                      const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
+                      float* row_sums, float* seeds, float* point_res, void* stream);
+
+/* Adam (torch.optim.Adam defaults semantics: bias-corrected, eps outside sqrt of v_hat), one launch. */
+int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/* Measures the sustained scalar-FFMA rate of this GPU (TFLOP/s); the FFMA kernels' roofline denominator. */
+int tde_fp32_peak_probe(double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDE_JET_H */

@@ -1,0 +1,12 @@
+"""torch_de_b200: the PINN residual hot path of torch_DE (jets forward, residual/loss, reverse to the
+weight gradient) as hand-written sm_100a CUDA behind torch_DE's own engine / loss API."""
+from .data import PINN_dict, PINN_group, make_batch
+from .de_getter import DE_Getter
+from .engine import Jet_engine, JetRunner
+from .equations import DE_func, get_derivatives, get_NavierStokes
+from .loss import Loss, Loss_handler
+from .networks import MLP, Sin, extract_layers
+from .spec import JetChannels, derivative_index_map
+
+__all__ = ['DE_Getter', 'Jet_engine', 'JetRunner', 'JetChannels', 'derivative_index_map', 'MLP', 'Sin', 'extract_layers',
+           'DE_func', 'get_derivatives', 'get_NavierStokes', 'Loss', 'Loss_handler', 'PINN_dict', 'PINN_group', 'make_batch']

@@ -1,0 +1,290 @@
+// Shared pieces of the sm_100a jet kernels: compile-time jet spec, activation jets and their
+// adjoints, mbarrier + bulk-async (TMA 1-D) helpers, and the kernel parameter block.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "tde_jet.h"
+
+namespace tde {
+
+constexpr int kComputeThreads = 256;            // 8 compute warps
+constexpr int kThreads = kComputeThreads + 128;  // + 1 producer warpgroup (bulk-async weight streamer; donates registers)
+constexpr int kNT = 8;                          // neurons per thread in the GEMM phases
+constexpr int kKC = 8;                          // reduction rows per streamed weight chunk
+constexpr int kMaxStages = 4;
+
+// ---------------------------------------------------------------------------------------------
+// Compile-time jet spec.  NF first-order channels; SMASK selects second-order pairs (a<=b over the
+// first-order channels, enumerated (0,0),(0,1),..,(0,NF-1),(1,1),...).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int popc_c(int m) { return m == 0 ? 0 : (m & 1) + popc_c(m >> 1); }
+__host__ __device__ constexpr int pair_index(int nf, int a, int b) {
+    // rank of (a,b), a<=b, in row-major upper-triangular order
+    int idx = 0;
+    for (int i = 0; i < a; ++i) idx += nf - i;
+    return idx + (b - a);
+}
+__host__ __device__ constexpr int nth_set_bit(int mask, int n) {
+    int pos = 0;
+    while (true) {
+        if (mask & 1) {
+            if (n == 0) return pos;
+            --n;
+        }
+        mask >>= 1;
+        ++pos;
+    }
+}
+__host__ __device__ constexpr int pair_a_of(int nf, int idx) {
+    int a = 0;
+    while (idx >= nf - a) {
+        idx -= nf - a;
+        ++a;
+    }
+    return a;
+}
+__host__ __device__ constexpr int pair_b_of(int nf, int idx) {
+    int a = 0;
+    while (idx >= nf - a) {
+        idx -= nf - a;
+        ++a;
+    }
+    return a + idx;
+}
+
+template <int NF_, int SMASK_>
+struct JetSpecT {
+    static constexpr int NF = NF_;
+    static constexpr int SMASK = SMASK_;
+    static constexpr int NS = popc_c(SMASK_);
+    static constexpr int J = 1 + NF_ + NS;
+    static constexpr int PT = (J <= 5) ? 4 : 2;  // points per thread
+    static constexpr int PJ = PT * J;            // jet columns per thread (multiple of 4)
+    static constexpr int NV = PJ / 4;
+    static_assert(PJ % 4 == 0, "thread jet columns must vectorise to float4");
+    __host__ __device__ static constexpr int pa(int q) { return pair_a_of(NF_, nth_set_bit(SMASK_, q)); }
+    __host__ __device__ static constexpr int pb(int q) { return pair_b_of(NF_, nth_set_bit(SMASK_, q)); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kernel parameter block (passed by value, __grid_constant__)
+// ---------------------------------------------------------------------------------------------
+struct JetParams {
+    const float* x;  // [B][d_in]
+    int64_t B;
+    int64_t n_tiles;
+    int d_in, n_out, L;  // L = number of ACTIVATED layers (>= 1)
+    int W;               // padded hidden width (multiple of 64)
+    int act;
+    int PG;     // point groups per tile (tile points = PG * PT)
+    int pitch;  // smem row pitch in floats (tile columns + pad, == 4 mod 8)
+    int n_stages;
+    int first_in[TDE_MAX_FIRST];
+    // packed weights (workspace)
+    const float* w_in;       // [W][d_in]
+    const float* b_in;       // [W]
+    const float* wt_hidden;  // [(L-1)][k=W][q=W]  forward operand:  Wt[k][q] = W_l[n(q)][k]
+    const float* wn_hidden;  // [(L-1)][n=W][q=W]  reverse operand:  Wn[n][q] = W_l[n][k(q)]
+    const float* b_hidden;   // [(L-1)][W]
+    const float* w_out;      // [n_out][W]
+    const float* b_out;      // [n_out]
+    // streams
+    float* out;
+    int64_t ld_out;
+    float* stash;  // [L][n_tiles][W][TP*J] or nullptr
+    const float* seeds;
+    int64_t ld_seeds;
+    // backward partial gradients
+    float* gpart;  // [n_ctas][gp_stride]
+    int64_t gp_stride;
+    int64_t gp_off_b_in, gp_off_hidden, gp_off_b_hidden, gp_off_w_out, gp_off_b_out;
+    int kblk;    // k rows per dW block
+    int rsplit;  // row (reduction) split of the dW phase
+};
+
+// column permutation of the packed weight matrices: thread group g (0..NG-1) owns neurons
+// n = g + NG*j (j = 0..7) and reads them as two float4 at q = 4g + (j&3) + (j>>2)*(W/2).
+__host__ __device__ inline int neuron_of_q(int q, int W) {
+    const int NG = W / kNT;
+    const int half = q >= W / 2;
+    const int qq = q - half * (W / 2);
+    const int g = qq >> 2;
+    const int j = (qq & 3) + 4 * half;
+    return g + NG * j;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, bulk async copy (TMA 1-D: SASS UBLKCP), named barriers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// barrier over the 256 compute threads only (the producer warp never joins it)
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// Activation jets.  h[0] value, h[1..NF] first order, h[1+NF..] second order (pairs pa/pb).
+// sigma', sigma'', sigma''' from the stashed channel-0 quantity: tanh stores t = tanh(h0), sin stores h0.
+// ---------------------------------------------------------------------------------------------
+struct Sig {
+    float s0, s1, s2, s3;
+};
+__device__ __forceinline__ Sig sig_from_pre(int act, float h0, float& stash0) {
+    Sig s;
+    if (act == TDE_ACT_TANH) {
+        const float t = tanhf(h0);
+        s.s0 = t;
+        s.s1 = fmaf(-t, t, 1.0f);
+        s.s2 = -2.0f * t * s.s1;
+        s.s3 = -2.0f * s.s1 * fmaf(-3.0f * t, t, 1.0f);
+        stash0 = t;
+    } else {
+        float sn, cs;
+        sincosf(h0, &sn, &cs);
+        s.s0 = sn;
+        s.s1 = cs;
+        s.s2 = -sn;
+        s.s3 = -cs;
+        stash0 = h0;
+    }
+    return s;
+}
+__device__ __forceinline__ Sig sig_from_stash(int act, float st0) {
+    Sig s;
+    if (act == TDE_ACT_TANH) {
+        const float t = st0;
+        s.s0 = t;
+        s.s1 = fmaf(-t, t, 1.0f);
+        s.s2 = -2.0f * t * s.s1;
+        s.s3 = -2.0f * s.s1 * fmaf(-3.0f * t, t, 1.0f);
+    } else {
+        float sn, cs;
+        sincosf(st0, &sn, &cs);
+        s.s0 = sn;
+        s.s1 = cs;
+        s.s2 = -sn;
+        s.s3 = -cs;
+    }
+    return s;
+}
+
+// z = act-jet(h); h[0] is replaced by the value to stash (t or h0); h[c>0] unchanged (they are stashed as is)
+template <class S>
+__device__ __forceinline__ void act_forward(int act, float (&h)[S::J], float (&z)[S::J]) {
+    float st0;
+    const Sig s = sig_from_pre(act, h[0], st0);
+    z[0] = s.s0;
+#pragma unroll
+    for (int a = 0; a < S::NF; ++a) z[1 + a] = s.s1 * h[1 + a];
+#pragma unroll
+    for (int q = 0; q < S::NS; ++q)
+        z[1 + S::NF + q] = fmaf(s.s2 * h[1 + S::pa(q)], h[1 + S::pb(q)], s.s1 * h[1 + S::NF + q]);
+    h[0] = st0;
+}
+
+// recompute z from the stashed (st0, h_c)
+template <class S>
+__device__ __forceinline__ void act_recompute(int act, const float (&st)[S::J], float (&z)[S::J]) {
+    const Sig s = sig_from_stash(act, st[0]);
+    z[0] = s.s0;
+#pragma unroll
+    for (int a = 0; a < S::NF; ++a) z[1 + a] = s.s1 * st[1 + a];
+#pragma unroll
+    for (int q = 0; q < S::NS; ++q)
+        z[1 + S::NF + q] = fmaf(s.s2 * st[1 + S::pa(q)], st[1 + S::pb(q)], s.s1 * st[1 + S::NF + q]);
+}
+
+// adjoint: given zb = dL/dz (jet) and the stash (st0, h_c) produce hb = dL/dh (jet), optionally z too
+template <class S, bool WANT_Z>
+__device__ __forceinline__ void act_backward(int act, const float (&st)[S::J], const float (&zb)[S::J],
+                                             float (&hb)[S::J], float (&z)[S::J]) {
+    const Sig s = sig_from_stash(act, st[0]);
+    float h0b = s.s1 * zb[0];
+#pragma unroll
+    for (int a = 0; a < S::NF; ++a) {
+        hb[1 + a] = s.s1 * zb[1 + a];
+        h0b = fmaf(s.s2 * st[1 + a], zb[1 + a], h0b);
+    }
+#pragma unroll
+    for (int q = 0; q < S::NS; ++q) {
+        const int ia = 1 + S::pa(q), ib = 1 + S::pb(q), iq = 1 + S::NF + q;
+        const float zq = zb[iq];
+        hb[iq] = s.s1 * zq;
+        hb[ia] = fmaf(s.s2 * st[ib], zq, hb[ia]);
+        hb[ib] = fmaf(s.s2 * st[ia], zq, hb[ib]);
+        h0b = fmaf(fmaf(s.s3 * st[ia], st[ib], s.s2 * st[iq]), zq, h0b);
+    }
+    hb[0] = h0b;
+    if (WANT_Z) {
+        z[0] = s.s0;
+#pragma unroll
+        for (int a = 0; a < S::NF; ++a) z[1 + a] = s.s1 * st[1 + a];
+#pragma unroll
+        for (int q = 0; q < S::NS; ++q)
+            z[1 + S::NF + q] = fmaf(s.s2 * st[1 + S::pa(q)], st[1 + S::pb(q)], s.s1 * st[1 + S::NF + q]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The register-tile GEMM shared by the forward pass and the reverse dX pass:
+//   acc[pc][j] += sum_k A[k][col0+pc] * Bq[k][q(g,j)]      (A: smem tile, K-major; Bq: streamed chunks)
+// Consumers wait on full[stage], compute kKC reduction rows, release with one arrive per warp.
+// ---------------------------------------------------------------------------------------------
+template <int PJ>
+__device__ __forceinline__ void gemm_chunk(float (&acc)[PJ][kNT], const float* __restrict__ Arow,
+                                           const float* __restrict__ wchunk, int pitch, int W, int g) {
+    constexpr int NV = PJ / 4;
+#pragma unroll
+    for (int kk = 0; kk < kKC; ++kk) {
+        float a[PJ];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 t = *reinterpret_cast<const float4*>(Arow + kk * pitch + 4 * v);
+            a[4 * v + 0] = t.x;
+            a[4 * v + 1] = t.y;
+            a[4 * v + 2] = t.z;
+            a[4 * v + 3] = t.w;
+        }
+        const float4 w0 = *reinterpret_cast<const float4*>(wchunk + kk * W + 4 * g);
+        const float4 w1 = *reinterpret_cast<const float4*>(wchunk + kk * W + (W >> 1) + 4 * g);
+        const float w[kNT] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int pc = 0; pc < PJ; ++pc)
+#pragma unroll
+            for (int j = 0; j < kNT; ++j) acc[pc][j] = fmaf(a[pc], w[j], acc[pc][j]);
+    }
+}
+
+}  // namespace tde

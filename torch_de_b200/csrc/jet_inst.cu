@@ -1,0 +1,27 @@
+// One translation unit per compiled jet spec: built with -DTDE_NF=<n> -DTDE_SMASK=<mask>.
+#include "jet_forward.cuh"
+#include "jet_backward.cuh"
+#include "jet_launch.h"
+
+#define TDE_CAT_(a, b, c, d) a##b##_##d
+#define TDE_CAT(a, b, c, d) TDE_CAT_(a, b, c, d)
+
+namespace tde {
+
+cudaError_t TDE_CAT(launch_forward_, TDE_NF, _, TDE_SMASK)(const JetParams& p, int grid, int smem, cudaStream_t st) {
+    auto k = jet_forward_kernel<TDE_NF, TDE_SMASK>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t TDE_CAT(launch_backward_, TDE_NF, _, TDE_SMASK)(const JetParams& p, int grid, int smem, cudaStream_t st) {
+    auto k = jet_backward_kernel<TDE_NF, TDE_SMASK>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace tde

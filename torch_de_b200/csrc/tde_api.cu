@@ -1,0 +1,629 @@
+// C ABI of libtde_jet.so (see include/tde_jet.h): planning, weight packing, kernel dispatch,
+// deterministic second-stage gradient reduction, fused residual/loss, Adam, FP32 peak probe.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "jet_launch.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define TDE_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(e__));   \
+    } while (0)
+
+constexpr int kSmemLimit = 232448;  // 227 KB opt-in per CTA on sm_100
+
+struct Dispatch {
+    int nf, smask;
+    tde::JetLauncher fwd, bwd;
+};
+#define TDE_ROW(nf, sm) {nf, sm, tde::launch_forward_##nf##_##sm, tde::launch_backward_##nf##_##sm},
+const Dispatch kDispatch[] = {TDE_SPEC_LIST(TDE_ROW)};
+#undef TDE_ROW
+
+const Dispatch* find_dispatch(int nf, int smask) {
+    for (const Dispatch& d : kDispatch)
+        if (d.nf == nf && d.smask == smask) return &d;
+    return nullptr;
+}
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// Everything derived from (net, spec, n_points): geometry + workspace offsets (in floats).
+struct Geometry {
+    int nf, smask, J, PT, PJ;
+    int width, W, L, d_in, n_out, act;
+    int PG, TP, pitch, stages_fwd, stages_bwd, kblk, rsplit;
+    int smem_fwd, smem_bwd;
+    int n_ctas;
+    int64_t n_tiles;
+    // packed weight offsets
+    int64_t o_w_in, o_b_in, o_wt, o_wn, o_bh, o_wo, o_bo, packed_floats;
+    // per-CTA partial gradient slab
+    int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo, gp_stride;
+    int64_t o_gpart;
+    int64_t workspace_floats;
+    int64_t stash_floats;
+    int64_t n_params;
+    const Dispatch* disp;
+};
+
+int sm_count() {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+        cached = n;
+    } else {
+        (void)cudaGetLastError();
+        cached = 148;  // planning without a device (unit tests on CPU): B200 has 148 SMs
+    }
+    return cached;
+}
+
+int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry* G) {
+    if (!net || !spec) return fail("null net/spec");
+    if (net->n_layers < 2 || net->n_layers > TDE_MAX_LAYERS)
+        return fail("need 2..%d Linear layers, got %d", TDE_MAX_LAYERS, net->n_layers);
+    const int L = net->n_layers - 1;
+    const int width = net->layers[0].out_features;
+    const int act = net->layers[0].act;
+    if (act != TDE_ACT_TANH && act != TDE_ACT_SIN) return fail("unsupported activation code %d (tanh/sin only)", act);
+    if (net->layers[0].in_features != spec->d_in) return fail("layer 0 in_features %d != d_in %d", net->layers[0].in_features, spec->d_in);
+    if (spec->d_in < 1 || spec->d_in > TDE_MAX_IN) return fail("d_in %d out of range 1..%d", spec->d_in, TDE_MAX_IN);
+    if (spec->n_out < 1 || spec->n_out > TDE_MAX_OUT) return fail("n_out %d out of range 1..%d", spec->n_out, TDE_MAX_OUT);
+    for (int l = 0; l < net->n_layers; ++l) {
+        const TdeLayer& ly = net->layers[l];
+        if (!ly.weight || !ly.bias) return fail("layer %d: weight and bias are required", l);
+        if (l < L) {
+            if (ly.out_features != width) return fail("hidden widths must all be equal (layer %d has %d, expected %d)", l, ly.out_features, width);
+            if (ly.act != act) return fail("all hidden activations must match");
+            if (l > 0 && ly.in_features != width) return fail("layer %d in_features %d != width %d", l, ly.in_features, width);
+        } else {
+            if (ly.act != TDE_ACT_NONE) return fail("last layer must be linear");
+            if (ly.in_features != width || ly.out_features != spec->n_out) return fail("output layer shape mismatch");
+        }
+    }
+    if (spec->n_first < 0 || spec->n_first > TDE_MAX_FIRST) return fail("n_first %d out of range", spec->n_first);
+    if (spec->n_second < 0 || spec->n_second > TDE_MAX_SECOND) return fail("n_second %d out of range", spec->n_second);
+    for (int a = 0; a < spec->n_first; ++a)
+        if (spec->first_in[a] < 0 || spec->first_in[a] >= spec->d_in) return fail("first_in[%d]=%d is not an input column", a, spec->first_in[a]);
+    int smask = 0, prev = -1;
+    for (int q = 0; q < spec->n_second; ++q) {
+        const int a = spec->second_a[q], b = spec->second_b[q];
+        if (a < 0 || b < a || b >= spec->n_first) return fail("second-order pair (%d,%d) must satisfy 0<=a<=b<n_first", a, b);
+        const int idx = tde::pair_index(spec->n_first, a, b);
+        if (idx <= prev) return fail("second-order pairs must be sorted and unique");
+        prev = idx;
+        smask |= 1 << idx;
+    }
+    const Dispatch* d = find_dispatch(spec->n_first, smask);
+    if (!d) return fail("jet spec (n_first=%d, pair mask=0x%x) is not compiled in; canonicalise on the host", spec->n_first, smask);
+
+    Geometry g{};
+    g.disp = d;
+    g.nf = spec->n_first;
+    g.smask = smask;
+    g.J = 1 + spec->n_first + spec->n_second;
+    g.PT = g.J <= 5 ? 4 : 2;
+    g.PJ = g.PT * g.J;
+    g.width = width;
+    g.L = L;
+    g.d_in = spec->d_in;
+    g.n_out = spec->n_out;
+    g.act = act;
+    g.W = width <= 256 ? (int)align_up(width, 64) : (int)align_up(width, 256);
+    if (g.W > 2048) return fail("hidden width %d too large (max 2048)", width);
+    const int NG = g.W / tde::kNT;
+    const int pg_max = std::max(1, tde::kComputeThreads / NG);
+    const int NI = std::min(g.W / 8, 32);
+    g.kblk = 64;
+    const int KI = g.kblk / 8;
+    g.rsplit = std::max(1, tde::kComputeThreads / (NI * KI));
+    bool found = false;
+    for (int pg = pg_max; pg >= 1 && !found; --pg) {
+        if (pg % g.rsplit != 0) continue;
+        const int TP = pg * g.PT;
+        const int cols = TP * g.J;
+        const int pitch = cols + ((cols % 8 == 4) ? 0 : 4);
+        const int64_t common = (int64_t)g.n_out * g.W + (int64_t)TP * g.d_in + (int64_t)g.J * g.n_out * TP;
+        for (int sb = tde::kMaxStages; sb >= 2 && !found; --sb) {
+            const int64_t ub = std::max<int64_t>({(int64_t)sb * tde::kKC * g.W, (int64_t)g.kblk * pitch, (int64_t)pg * g.n_out * g.W});
+            const int64_t smem_b = 128 + 4 * ((int64_t)g.W * pitch + ub + common);
+            if (smem_b > kSmemLimit) continue;
+            int sf = tde::kMaxStages;
+            int64_t smem_f = 0;
+            for (; sf >= 2; --sf) {
+                smem_f = 128 + 4 * ((int64_t)g.W * pitch + (int64_t)sf * tde::kKC * g.W + common);
+                if (smem_f <= kSmemLimit) break;
+            }
+            if (sf < 2) continue;
+            g.PG = pg;
+            g.TP = TP;
+            g.pitch = pitch;
+            g.stages_fwd = sf;
+            g.stages_bwd = sb;
+            g.smem_fwd = (int)smem_f;
+            g.smem_bwd = (int)smem_b;
+            found = true;
+        }
+    }
+    if (!found) {
+        // rsplit may not divide any feasible PG for exotic shapes: fall back to rsplit = 1
+        return fail("no tile configuration fits shared memory for width %d, J %d", width, g.J);
+    }
+    g.n_tiles = B > 0 ? (B + g.TP - 1) / g.TP : 0;
+    g.n_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), g.n_tiles));
+
+    const int64_t WW = (int64_t)g.W * g.W;
+    int64_t o = 0;
+    g.o_w_in = o; o = align_up(o + (int64_t)g.W * g.d_in, 4);
+    g.o_b_in = o; o = align_up(o + g.W, 4);
+    g.o_wt = o;   o += (int64_t)(L - 1) * WW;
+    g.o_wn = o;   o += (int64_t)(L - 1) * WW;
+    g.o_bh = o;   o += (int64_t)(L - 1) * g.W;
+    g.o_wo = o;   o = align_up(o + (int64_t)g.n_out * g.W, 4);
+    g.o_bo = o;   o = align_up(o + g.n_out, 4);
+    g.packed_floats = align_up(o, 64);
+
+    int64_t q = 0;
+    q = align_up((int64_t)g.W * g.d_in, 4);
+    g.g_b_in = q;   q = align_up(q + g.W, 4);
+    g.g_hidden = q; q += (int64_t)(L - 1) * g.rsplit * WW;
+    g.g_bh = q;     q += (int64_t)(L - 1) * g.W;
+    g.g_wo = q;     q = align_up(q + (int64_t)g.n_out * g.W, 4);
+    g.g_bo = q;     q = align_up(q + g.n_out, 4);
+    g.gp_stride = q;
+    g.o_gpart = g.packed_floats;
+    g.workspace_floats = g.packed_floats + (int64_t)g.n_ctas * g.gp_stride;
+    g.stash_floats = (int64_t)L * g.n_tiles * g.W * g.TP * g.J;
+
+    int64_t np = 0;
+    for (int l = 0; l < net->n_layers; ++l)
+        np += (int64_t)net->layers[l].in_features * net->layers[l].out_features + net->layers[l].out_features;
+    g.n_params = np;
+    *G = g;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: pad to W, transpose / permute columns for the register-tile GEMMs
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+    TdeNet net;
+    int W, L, d_in, n_out, width;
+    int64_t o_w_in, o_b_in, o_wt, o_wn, o_bh, o_wo, o_bo, total;
+    int want_wt, want_wn;
+};
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* __restrict__ ws) {
+    const int W = a.W;
+    const int64_t WW = (int64_t)W * W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.total; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.0f;
+        if (i < a.o_b_in) {  // w_in [W][d_in]
+            const int64_t r = i - a.o_w_in;
+            if (r < (int64_t)W * a.d_in) {
+                const int n = (int)(r / a.d_in), c = (int)(r % a.d_in);
+                if (n < a.width) v = a.net.layers[0].weight[(int64_t)n * a.d_in + c];
+            }
+        } else if (i < a.o_wt) {  // b_in
+            const int n = (int)(i - a.o_b_in);
+            if (n < a.width) v = a.net.layers[0].bias[n];
+        } else if (i < a.o_wn) {  // Wt[l][k][q] = W_l[n(q)][k]
+            if (!a.want_wt) continue;
+            const int64_t r = i - a.o_wt;
+            const int l = (int)(r / WW) + 1;
+            const int k = (int)((r % WW) / W), q = (int)(r % W);
+            const int n = tde::neuron_of_q(q, W);
+            if (n < a.width && k < a.width) v = a.net.layers[l].weight[(int64_t)n * a.width + k];
+        } else if (i < a.o_bh) {  // Wn[l][n][q] = W_l[n][k(q)]
+            if (!a.want_wn) continue;
+            const int64_t r = i - a.o_wn;
+            const int l = (int)(r / WW) + 1;
+            const int n = (int)((r % WW) / W), q = (int)(r % W);
+            const int k = tde::neuron_of_q(q, W);
+            if (n < a.width && k < a.width) v = a.net.layers[l].weight[(int64_t)n * a.width + k];
+        } else if (i < a.o_wo) {  // b_hidden
+            const int64_t r = i - a.o_bh;
+            const int l = (int)(r / W) + 1, n = (int)(r % W);
+            if (n < a.width) v = a.net.layers[l].bias[n];
+        } else if (i < a.o_bo) {  // w_out [n_out][W]
+            const int64_t r = i - a.o_wo;
+            if (r < (int64_t)a.n_out * W) {
+                const int o = (int)(r / W), k = (int)(r % W);
+                if (k < a.width) v = a.net.layers[a.L].weight[(int64_t)o * a.width + k];
+            }
+        } else {
+            const int o = (int)(i - a.o_bo);
+            if (o < a.n_out) v = a.net.layers[a.L].bias[o];
+        }
+        ws[i] = v;
+    }
+}
+
+int launch_pack(const TdeNet* net, const Geometry& g, float* ws, bool want_wt, bool want_wn, cudaStream_t st) {
+    PackArgs a{};
+    a.net = *net;
+    a.W = g.W; a.L = g.L; a.d_in = g.d_in; a.n_out = g.n_out; a.width = g.width;
+    a.o_w_in = g.o_w_in; a.o_b_in = g.o_b_in; a.o_wt = g.o_wt; a.o_wn = g.o_wn; a.o_bh = g.o_bh;
+    a.o_wo = g.o_wo; a.o_bo = g.o_bo; a.total = g.packed_floats;
+    a.want_wt = want_wt; a.want_wn = want_wn;
+    const int threads = 256;
+    const int blocks = (int)std::min<int64_t>((g.packed_floats + threads - 1) / threads, 148 * 8);
+    pack_weights_kernel<<<blocks, threads, 0, st>>>(a, ws);
+    TDE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+void fill_params(const Geometry& g, const TdeJetSpec* spec, float* ws, tde::JetParams* p) {
+    memset(p, 0, sizeof *p);
+    p->d_in = g.d_in; p->n_out = g.n_out; p->L = g.L; p->W = g.W; p->act = g.act;
+    p->PG = g.PG; p->pitch = g.pitch; p->n_tiles = g.n_tiles;
+    for (int a = 0; a < TDE_MAX_FIRST; ++a) p->first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
+    p->w_in = ws + g.o_w_in; p->b_in = ws + g.o_b_in; p->wt_hidden = ws + g.o_wt; p->wn_hidden = ws + g.o_wn;
+    p->b_hidden = ws + g.o_bh; p->w_out = ws + g.o_wo; p->b_out = ws + g.o_bo;
+    p->gpart = ws + g.o_gpart; p->gp_stride = g.gp_stride;
+    p->gp_off_b_in = g.g_b_in; p->gp_off_hidden = g.g_hidden; p->gp_off_b_hidden = g.g_bh;
+    p->gp_off_w_out = g.g_wo; p->gp_off_b_out = g.g_bo;
+    p->kblk = g.kblk; p->rsplit = g.rsplit;
+}
+
+// ---------------------------------------------------------------------------------------------
+// second-stage reduction: flat_grad[i] += scale * sum_{cta (, split)} slab[cta][map(i)]   (fixed order)
+// ---------------------------------------------------------------------------------------------
+struct ReduceArgs {
+    int n_layers, W, width, d_in, n_out, rsplit, n_active;
+    int64_t n_params, gp_stride;
+    int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo;
+    float scale;
+};
+
+__global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const float* __restrict__ gpart,
+                                    float* __restrict__ flat) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= a.n_params) return;
+    // decode flat index -> (layer, weight|bias, row, col)
+    int64_t r = i;
+    int64_t src = -1;
+    int splits = 1;
+    const int L = a.n_layers - 1;
+    const int64_t WW = (int64_t)a.W * a.W;
+    // layer 0
+    const int64_t n0 = (int64_t)a.width * a.d_in;
+    if (r < n0) {
+        src = (r / a.d_in) * a.d_in + (r % a.d_in);  // slab w_in is [W][d_in] with the same row pitch
+    } else if ((r -= n0) < a.width) {
+        src = a.g_b_in + r;
+    } else {
+        r -= a.width;
+        const int64_t per = (int64_t)a.width * a.width + a.width;
+        const int64_t hid = (int64_t)(L - 1) * per;
+        if (r < hid) {
+            const int l = (int)(r / per);
+            const int64_t rr = r % per;
+            if (rr < (int64_t)a.width * a.width) {
+                const int n = (int)(rr / a.width), k = (int)(rr % a.width);
+                src = a.g_hidden + (int64_t)l * a.rsplit * WW + (int64_t)n * a.W + k;
+                splits = a.rsplit;
+            } else {
+                src = a.g_bh + (int64_t)l * a.W + (rr - (int64_t)a.width * a.width);
+            }
+        } else {
+            r -= hid;
+            const int64_t nwo = (int64_t)a.n_out * a.width;
+            if (r < nwo) {
+                src = a.g_wo + (r / a.width) * a.W + (r % a.width);
+            } else {
+                src = a.g_bo + (r - nwo);
+            }
+        }
+    }
+    float s = 0.0f;
+    for (int c = 0; c < a.n_active; ++c) {
+        const float* slab = gpart + (int64_t)c * a.gp_stride + src;
+        for (int q = 0; q < splits; ++q) s += slab[(int64_t)q * WW];
+    }
+    flat[i] += a.scale * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused residual + loss: register-program interpreter, forward then reverse sweep per point
+// ---------------------------------------------------------------------------------------------
+constexpr int kLossBlocks = 592;  // 148 SMs x 4
+constexpr int kLossThreads = 256;
+
+__device__ float g_loss_partials[kLossBlocks * TDE_MAX_ROWS];
+__device__ unsigned int g_loss_ticket = 0;
+
+__global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
+    const __grid_constant__ TdeLossProgram prog, const float* __restrict__ streams, int64_t ld, int n_stream_rows,
+    const float* __restrict__ aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
+    float* __restrict__ row_sums, float* __restrict__ seeds, float* __restrict__ point_res) {
+    __shared__ float red[TDE_MAX_ROWS][kLossThreads / 32];
+    __shared__ bool is_last;
+    float part[TDE_MAX_ROWS];
+#pragma unroll
+    for (int r = 0; r < TDE_MAX_ROWS; ++r) part[r] = 0.0f;
+
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = p0 + i;
+        float v[TDE_MAX_REGS], adj[TDE_MAX_REGS];
+        for (int k = 0; k < prog.n_ops; ++k) {
+            const TdeOp op = prog.ops[k];
+            float r;
+            switch (op.op) {
+                case TDE_OP_CONST: r = op.imm; break;
+                case TDE_OP_LOAD: r = streams[(int64_t)op.a * ld + p]; break;
+                case TDE_OP_AUX: r = aux[(int64_t)op.a * ld_aux + i]; break;
+                case TDE_OP_ADD: r = v[op.a] + v[op.b]; break;
+                case TDE_OP_SUB: r = v[op.a] - v[op.b]; break;
+                case TDE_OP_MUL: r = v[op.a] * v[op.b]; break;
+                case TDE_OP_NEG: r = -v[op.a]; break;
+                case TDE_OP_POWI: {
+                    const int e = (int)op.imm;
+                    float b = v[op.a];
+                    r = 1.0f;
+                    for (int t = 0; t < (e < 0 ? -e : e); ++t) r *= b;
+                    if (e < 0) r = 1.0f / r;
+                } break;
+                case TDE_OP_ABS: r = fabsf(v[op.a]); break;
+                case TDE_OP_SIN: r = sinf(v[op.a]); break;
+                case TDE_OP_COS: r = cosf(v[op.a]); break;
+                case TDE_OP_DIV: r = v[op.a] / v[op.b]; break;
+                default: r = 0.0f;
+            }
+            v[op.dst] = r;
+            adj[op.dst] = 0.0f;
+        }
+        for (int r = 0; r < prog.n_rows; ++r) {
+            const float res = v[prog.res_reg[r]];
+            const float w = prog.w_aux[r] >= 0 ? aux[(int64_t)prog.w_aux[r] * ld_aux + i] : prog.w_const[r];
+            part[r] += w * res * res;
+            adj[prog.res_reg[r]] += prog.coef[r] * inv_count * 2.0f * w * res;
+            if (point_res) point_res[(int64_t)r * n + i] = res;
+        }
+        if (seeds) {
+            for (int s = 0; s < n_stream_rows; ++s) seeds[(int64_t)s * ld + p] = 0.0f;
+            for (int k = prog.n_ops - 1; k >= 0; --k) {
+                const TdeOp op = prog.ops[k];
+                const float d = adj[op.dst];
+                switch (op.op) {
+                    case TDE_OP_LOAD: seeds[(int64_t)op.a * ld + p] += d; break;
+                    case TDE_OP_ADD: adj[op.a] += d; adj[op.b] += d; break;
+                    case TDE_OP_SUB: adj[op.a] += d; adj[op.b] -= d; break;
+                    case TDE_OP_MUL: {
+                        const float va = v[op.a], vb = v[op.b];
+                        adj[op.a] += d * vb;
+                        adj[op.b] += d * va;
+                    } break;
+                    case TDE_OP_NEG: adj[op.a] -= d; break;
+                    case TDE_OP_POWI: {
+                        const int e = (int)op.imm;
+                        const float b = v[op.a];
+                        float pw = 1.0f;  // b^(e-1)
+                        for (int t = 0; t < (e - 1 < 0 ? 1 - e : e - 1); ++t) pw *= b;
+                        if (e - 1 < 0) pw = 1.0f / pw;
+                        adj[op.a] += d * (float)e * pw;
+                    } break;
+                    case TDE_OP_ABS: adj[op.a] += v[op.a] >= 0.0f ? d : -d; break;
+                    case TDE_OP_SIN: adj[op.a] += d * cosf(v[op.a]); break;
+                    case TDE_OP_COS: adj[op.a] -= d * sinf(v[op.a]); break;
+                    case TDE_OP_DIV: {
+                        const float inv = 1.0f / v[op.b];
+                        adj[op.a] += d * inv;
+                        adj[op.b] -= d * v[op.dst] * inv;
+                    } break;
+                    default: break;
+                }
+            }
+        }
+    }
+    // block reduction (fixed order), then last-block-done cross-block reduction (fixed order)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < TDE_MAX_ROWS; ++r) {
+        float s = part[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[r][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < TDE_MAX_ROWS) {
+        float s = 0.0f;
+        for (int w = 0; w < kLossThreads / 32; ++w) s += red[threadIdx.x][w];
+        g_loss_partials[blockIdx.x * TDE_MAX_ROWS + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&g_loss_ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (threadIdx.x < prog.n_rows) {
+            float s = 0.0f;
+            for (unsigned b = 0; b < gridDim.x; ++b) s += g_loss_partials[b * TDE_MAX_ROWS + threadIdx.x];
+            row_sums[threadIdx.x] += s * inv_count;
+        }
+        if (threadIdx.x == 0) g_loss_ticket = 0;
+    }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;     // exp_avg.lerp_(grad, 1-beta1)
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] -= (lr / bc1) * (mi / denom);
+    }
+}
+
+__global__ void __launch_bounds__(512) ffma_probe_kernel(float* out, int iters, float a, float b) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-6f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tde_last_error(void) { return g_err.c_str(); }
+int tde_version(void) { return 100; }
+
+int tde_plan(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points, TdePlan* plan) {
+    if (!plan) return fail("null plan");
+    Geometry g;
+    if (int rc = make_geometry(net, spec, n_points, &g)) return rc;
+    plan->n_channels = g.J;
+    plan->width_padded = g.W;
+    plan->tile_points = g.TP;
+    plan->n_ctas = g.n_ctas;
+    plan->n_tiles = g.n_tiles;
+    plan->stash_bytes = g.stash_floats * 4;
+    plan->workspace_bytes = g.workspace_floats * 4;
+    plan->n_params = g.n_params;
+    plan->smem_forward = g.smem_fwd;
+    plan->smem_backward = g.smem_bwd;
+    return 0;
+}
+
+int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points, float* out,
+                    int64_t ld_out, float* stash, void* workspace, void* stream) {
+    Geometry g;
+    if (int rc = make_geometry(net, spec, n_points, &g)) return rc;
+    if (n_points == 0) return 0;
+    if (!x || !out || !workspace) return fail("null x/out/workspace");
+    if (ld_out < n_points) return fail("ld_out %lld < n_points %lld", (long long)ld_out, (long long)n_points);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = (float*)workspace;
+    if (int rc = launch_pack(net, g, ws, true, false, st)) return rc;
+    tde::JetParams p;
+    fill_params(g, spec, ws, &p);
+    p.x = x; p.B = n_points; p.out = out; p.ld_out = ld_out; p.stash = stash; p.n_stages = g.stages_fwd;
+    TDE_CUDA(g.disp->fwd(p, g.n_ctas, g.smem_fwd, st));
+    return 0;
+}
+
+int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points, const float* stash,
+                     const float* seeds, int64_t ld_seeds, float grad_scale, float* flat_grad, void* workspace,
+                     void* stream) {
+    Geometry g;
+    if (int rc = make_geometry(net, spec, n_points, &g)) return rc;
+    if (n_points == 0) return 0;
+    if (!x || !stash || !seeds || !flat_grad || !workspace) return fail("null x/stash/seeds/flat_grad/workspace");
+    if (ld_seeds < n_points) return fail("ld_seeds %lld < n_points %lld", (long long)ld_seeds, (long long)n_points);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = (float*)workspace;
+    if (int rc = launch_pack(net, g, ws, false, true, st)) return rc;
+    tde::JetParams p;
+    fill_params(g, spec, ws, &p);
+    p.x = x; p.B = n_points; p.stash = const_cast<float*>(stash); p.seeds = seeds; p.ld_seeds = ld_seeds;
+    p.n_stages = g.stages_bwd;
+    TDE_CUDA(g.disp->bwd(p, g.n_ctas, g.smem_bwd, st));
+    ReduceArgs r{};
+    r.n_layers = net->n_layers; r.W = g.W; r.width = g.width; r.d_in = g.d_in; r.n_out = g.n_out;
+    r.rsplit = g.rsplit; r.n_active = g.n_ctas; r.n_params = g.n_params; r.gp_stride = g.gp_stride;
+    r.g_b_in = g.g_b_in; r.g_hidden = g.g_hidden; r.g_bh = g.g_bh; r.g_wo = g.g_wo; r.g_bo = g.g_bo;
+    r.scale = grad_scale;
+    const int threads = 256;
+    reduce_grads_kernel<<<(int)((g.n_params + threads - 1) / threads), threads, 0, st>>>(r, ws + g.o_gpart, flat_grad);
+    TDE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
+                      const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count, float* row_sums,
+                      float* seeds, float* point_res, void* stream) {
+    if (!prog || !streams || !row_sums) return fail("null program/streams/row_sums");
+    if (prog->n_ops < 1 || prog->n_ops > TDE_MAX_OPS) return fail("n_ops %d out of range", prog->n_ops);
+    if (prog->n_rows < 1 || prog->n_rows > TDE_MAX_ROWS) return fail("n_rows %d out of range", prog->n_rows);
+    for (int k = 0; k < prog->n_ops; ++k) {
+        const TdeOp& op = prog->ops[k];
+        if (op.dst < 0 || op.dst >= TDE_MAX_REGS) return fail("op %d: dst register %d out of range", k, op.dst);
+        if (op.op == TDE_OP_LOAD && (op.a < 0 || op.a >= n_stream_rows)) return fail("op %d: stream row %d out of range", k, op.a);
+        if (op.op == TDE_OP_AUX && !aux) return fail("op %d reads aux but aux is null", k);
+        if (op.op >= TDE_OP_ADD && (op.a < 0 || op.a >= TDE_MAX_REGS)) return fail("op %d: source register out of range", k);
+    }
+    if (n == 0) return 0;
+    const int blocks = (int)std::min<int64_t>((n + kLossThreads - 1) / kLossThreads, kLossBlocks);
+    residual_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(*prog, streams, ld, n_stream_rows, aux, ld_aux,
+                                                                             p0, n, inv_count, row_sums, seeds, point_res);
+    TDE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int32_t step, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("null adam buffer");
+    if (n == 0) return 0;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const int threads = 256;
+    const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 8);
+    adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                              (float)bc1, (float)sqrt(bc2));
+    TDE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tde_fp32_peak_probe(double* tflops, void* stream) {
+    if (!tflops) return fail("null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = sm_count();
+    const int threads = 512, grid = sms * 2, iters = 20000;
+    float* buf = nullptr;
+    TDE_CUDA(cudaMalloc(&buf, sizeof(float) * threads * grid));
+    cudaEvent_t e0, e1;
+    TDE_CUDA(cudaEventCreate(&e0));
+    TDE_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0, st);
+        ffma_probe_kernel<<<grid, threads, 0, st>>>(buf, iters, 1.0001f, 0.5f);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    TDE_CUDA(cudaGetLastError());
+    *tflops = 2.0 * 16 * iters * (double)threads * grid / (best * 1e-3) * 1e-12;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+"""Loss table with the reference's `Loss_handler` / `Loss` surface (src/torch_DE/utils/loss.py:18-313),
+without pandas: rows are plain records, so a training step does no DataFrame masking (`.loc/.apply`,
+loss.py:192-199, is the reference's dominant host cost at small batch sizes).
+
+Semantics kept: row loss = aggregate(weight * |residual|**power) with aggregate = mean|sum (loss.py:25-59);
+`sum()` adds the rows (:60-64); `grouped_losses(by)` sums rows per 'loss_type' | 'group' | 'variable' (:72-83).
+"""
+from typing import Callable, Dict, List, Union
+
+import torch
+from torch import Tensor
+
+from .equations import DE_func
+
+
+class GroupedLosses(dict):
+    """dict of name -> scalar Tensor; `.index` for code written against the pandas Series the reference returns."""
+    @property
+    def index(self):
+        return list(self.keys())
+
+
+class Loss:
+    def __init__(self, rows: List[dict], aggregation_method: str = 'mean', power: Union[int, None] = 2):
+        self.losses = rows
+        self.aggregation_method = aggregation_method
+        self.power = power
+        self._agg = torch.mean if aggregation_method == 'mean' else torch.sum
+        self._done = False
+
+    def error_func(self, r: Tensor) -> Tensor:
+        return torch.abs(r).pow(self.power) if self.power is not None else r
+
+    def point_error(self) -> List[Tensor]:
+        for row in self.losses:
+            if row.get('point_error') is None:
+                row['point_error'] = self.error_func(row['residual'])
+        return [row['point_error'] for row in self.losses]
+
+    def weighted_point_error(self) -> List[Tensor]:
+        self.point_error()
+        for row in self.losses:
+            if row.get('weighted_error') is None:
+                row['weighted_error'] = row['weighting'] * row['point_error']
+        return [row['weighted_error'] for row in self.losses]
+
+    def aggregated_loss(self) -> List[Tensor]:
+        if not self._done:
+            self.weighted_point_error()
+            for row in self.losses:
+                row['aggregated_loss'] = self._agg(row['weighted_error'])
+            self._done = True
+        return [row['aggregated_loss'] for row in self.losses]
+
+    def sum(self) -> Tensor:
+        return sum(self.aggregated_loss())
+
+    def individual_losses(self) -> Tensor:
+        return torch.stack(list(self.aggregated_loss()))
+
+    def grouped_losses(self, groupby: str) -> GroupedLosses:
+        if groupby not in ('loss_type', 'group', 'variable'):
+            raise ValueError(f'groupby must be one of the following strings: "loss_type", "group" or "variable". Got {groupby} instead')
+        self.aggregated_loss()
+        out = GroupedLosses()
+        for row in self.losses:
+            k = row[groupby]
+            out[k] = out[k] + row['aggregated_loss'] if k in out else row['aggregated_loss']
+        return out
+
+    def backward(self):
+        self.sum().backward()
+
+    def __len__(self):
+        return len(self.losses)
+
+    def print_losses(self, epoch, groupby='loss_type'):
+        total = self.sum()
+        if groupby is None:
+            names = [f"{r['loss_type']}__{r['group']}__{r['variable']}" for r in self.losses]
+            vals = self.aggregated_loss()
+        else:
+            g = self.grouped_losses(groupby)
+            names, vals = list(g.keys()), list(g.values())
+        body = '\t'.join(f'{n}: {float(v):.3E}' for n, v in zip(names, vals))
+        print(f'Epoch {epoch}:- Total Loss {float(total):.3E}\t {body}')
+
+
+class Loss_handler:
+    def __init__(self, dataset=None) -> None:
+        self.rows: List[dict] = []
+        self.update_dataset(dataset)
+
+    def update_dataset(self, dataset):
+        self.dataset = dataset
+        if dataset is None:
+            self._group_names = None
+        elif hasattr(dataset, 'group_names'):
+            self._group_names = list(dataset.group_names())
+        elif isinstance(dataset, dict):
+            self._group_names = list(dataset.keys())
+        else:
+            self._group_names = list(dataset)
+
+    def __len__(self):
+        return len(self.rows)
+
+    def __call__(self, group_input: Dict, group_output: Dict, **kwargs) -> Loss:
+        return self.calculate(group_input, group_output, **kwargs)
+
+    def calculate(self, batched_input, batched_output, power: int = 2, aggregation_method='mean') -> Loss:
+        rows = []
+        for spec in self.rows:
+            row = dict(spec)
+            if spec['custom']:
+                row['residual'] = spec['evaluation'](batched_input, batched_output)
+                row['weighting'] = 1.
+            else:
+                g = spec['group']
+                if g not in batched_input:
+                    continue
+                gi, go = batched_input[g], batched_output[g]
+                row['residual'] = spec['evaluation'](gi, go)
+                row['weighting'] = spec['weighting_function'](gi, go)
+            rows.append(row)
+        return Loss(rows, aggregation_method, power)
+
+    def set_terms(self, loss_type, group, var_dict: Dict[str, Callable], weighting, custom: bool = False):
+        if self._group_names is not None and not custom:
+            assert group in self._group_names, f"group '{group}' is not in the dataset"
+        if not isinstance(weighting, dict):
+            weighting = {k: weighting for k in var_dict}
+        for (var_name, fn), w in zip(var_dict.items(), weighting.values()):
+            if any(r['group'] == group and r['loss_type'] == loss_type and r['variable'] == var_name for r in self.rows):
+                raise ValueError(f'variable name {var_name} already exists in group {group} as a {loss_type} term')
+            wf = w if callable(w) else (lambda gi, go, _w=w: _w)
+            self.rows.append({'loss_type': loss_type, 'group': group, 'variable': var_name, 'evaluation': fn,
+                              'weighting_function': wf, 'weighting_spec': w, 'custom': custom})
+
+    @staticmethod
+    def create_residual_from_rhs(var_name, rhs):
+        rhs_func = rhs if callable(rhs) else DE_func(lambda _rhs=rhs, **kwargs: _rhs)
+        fn = lambda group_input, group_output: group_output[var_name] - rhs_func(group_input, group_output)  # noqa: E731
+        fn.rhs_spec = (var_name, rhs)
+        return fn
+
+    def add_boundary(self, group, bound_dict: Dict[str, Union[float, Callable]], weighting=1):
+        self.set_terms('boundary', group, {v: self.create_residual_from_rhs(v, rhs) for v, rhs in bound_dict.items()}, weighting)
+
+    def add_initial_condition(self, group: str, ic_dict: dict, weighting=1):
+        self.set_terms('initial condition', group, {v: self.create_residual_from_rhs(v, rhs) for v, rhs in ic_dict.items()}, weighting)
+
+    def add_residual(self, group, residuals: Dict[str, Callable], weighting=1):
+        self.set_terms('residual', group, residuals, weighting)
+
+    def add_data_constraint(self, loss_type, group, data_vars: List[str], weighting=1.):
+        def make(var_name):
+            return lambda gi, go: go[var_name] - gi.batchables[var_name]
+        self.set_terms(loss_type, group, {v: make(v) for v in data_vars}, weighting)
+
+    def add_periodic(self, group_1: str, group_2: str, variable: str):
+        def periodic(batched_input, batched_output):
+            return batched_output[group_1][variable] - batched_output[group_2][variable]
+        self.set_terms('periodic', group_1, {variable: periodic}, weighting=1., custom=True)
+
+    def add_custom_function(self, loss_type: str, group: str, func_dict: Dict[str, Callable]):
+        self.set_terms(loss_type, group, func_dict, weighting=1., custom=True)
