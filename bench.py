@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the PINN residual hot path (BASELINE.json metric: collocation points/sec per training step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ldc]
+
+One step = jets forward -> residual + boundary loss -> reverse to the weight gradient -> (all-reduce) -> Adam,
+through the public API (DE_Getter.calculate -> Loss_handler -> backward -> optimizer.step).
+Weak scaling: every rank holds `--points-per-gpu` collocation points (default 4e6/8, the LDC config of
+BASELINE.json spread over 8 GPUs); `value` is the whole-job points/s.
+
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port of its
+torch.func/autograd calls, oracle/ref_autograd.py) on this box's host cores on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "collocation points/sec per PINN training step (residual+grad)"
+UNIT = "points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ldc")
+    ap.add_argument("--points-per-gpu", type=int, default=0)
+    ap.add_argument("--boundary-per-gpu", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="collocation points per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(self.power) if self.power else None, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(workload, n_col, n_bnd, steps, warmup):
+    from oracle import ref_autograd as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    owl = O.WORKLOADS[workload]()
+    n = owl.net
+    params = [p.requires_grad_(True) for p in O.init_mlp_params(n["d_in"], n["n_out"], n["width"], n["n_act"], seed=1234)]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    groups = O.sample_groups(owl, n_col, n_bnd, seed=1234)
+    n_pts = sum(x.shape[0] for x in groups.values())
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = O.step(owl, params, groups)
+        for p, g in zip(params, res["grads"]):
+            p.grad = g
+        opt.step()
+        opt.zero_grad()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return n_pts, times, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n_bnd = max(1, args.cpu_sample // 64)
+    n_pts, times, cores = cpu_reference_steps(args.workload, args.cpu_sample, n_bnd, args.steps, args.warmup)
+    total = sum(times)
+    value = n_pts * len(times) / total
+    sample = f"{args.cpu_sample} collocation + {n_bnd} pts per boundary group per step, {len(times)} timed steps"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "device": "host CPU", "points_per_step": n_pts},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(w):
+    return {"ldc": "Tutorials/Lid_Driven_Cavity.py: steady 2D Navier-Stokes (u,v,p), MLP 8x256 tanh, 10 derivative names (J=5)",
+            "burgers": "Tutorials/Burgers1D.py: MLP 8x64 tanh (J=4)", "allen_cahn": "Tutorials/AllenCahn.py: MLP 6x128 tanh (J=4)",
+            "spring": "Tutorials/Spring.py: Sequential(1,200,1) tanh (J=3)",
+            "cylinder": "Tutorials/Stokes_Cylinder.py: steady 2D Navier-Stokes, MLP 10x512 tanh (J=5)"}[w]
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    import torch_de_b200 as T
+    from torch_de_b200 import _lib
+    from torch_de_b200 import workloads as WL
+    from torch_de_b200.dp import FlatGrads
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.lib()
+
+    wl = WL.WORKLOADS[args.workload]()
+    n_col = args.points_per_gpu or max(1, wl.default_points // 8)
+    n_bnd = args.boundary_per_gpu or max(1, wl.default_boundary // 8)
+    torch.manual_seed(1234)                                  # AllenCahn.py:23, Stokes_Cylinder.py:83
+    net = wl.make_net().to(dev)
+    pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+    runner = pinn.deriv_method._full
+    host_groups = {g: x.pin_memory() for g, x in wl.sample(n_col, n_bnd, seed=1234 + rank).items()}
+    dev_groups = {g: x.to(dev) for g, x in host_groups.items()}
+    batch = T.make_batch(wl.input_vars, dev_groups)
+    losses = wl.build_losses(list(dev_groups.keys()))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)        # Lid_Driven_Cavity.py:71
+    flat = FlatGrads(net)
+    n_pts_rank = sum(x.shape[0] for x in dev_groups.values())
+
+    def step(from_host=False):
+        if from_host:
+            for g, x in host_groups.items():
+                dev_groups[g].copy_(x, non_blocking=True)
+        out = pinn.calculate(batch)
+        loss = losses(batch, out)
+        total = wl.combine(loss.grouped_losses("loss_type"))
+        total.backward()
+        if world > 1:
+            flat.all_reduce_mean()
+        opt.step()
+        flat.zero()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(n_steps, from_host):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n_steps):
+            t = step(from_host)
+            if from_host:
+                t.item()          # device -> host read of the step's loss
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    launches0 = lib.tde_launch_count()
+    lib.tde_profile_begin()
+    with ClockSampler(local_rank) as clk:
+        ms_total = timed(args.steps, from_host=False)
+    launches = lib.tde_launch_count() - launches0
+    fwd_ms, bwd_ms = C.c_double(), C.c_double()
+    n_fwd, n_bwd = C.c_int32(), C.c_int32()
+    lib.tde_profile_end(C.byref(fwd_ms), C.byref(n_fwd), C.byref(bwd_ms), C.byref(n_bwd))
+
+    for _ in range(2):
+        step(True).item()
+    ms_e2e = timed(args.steps, from_host=True)
+
+    if rank != 0:
+        return
+    n_pts_job = n_pts_rank * world
+    value = n_pts_job * args.steps / (ms_total * 1e-3)
+    e2e_value = n_pts_job * args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel (reverse sweep: dX + dW = 4*J*sum(W_in*W_out) FLOP/pt)
+    peak = C.c_double()
+    _lib.check(lib.tde_fp32_peak_probe(C.byref(peak), None), "tde_fp32_peak_probe")
+    J = runner.ch.n_channels
+    f_pt = wl.flops_per_point(J)
+    bwd_avg_ms = bwd_ms.value / max(1, n_bwd.value)
+    fwd_avg_ms = fwd_ms.value / max(1, n_fwd.value)
+    ach_bwd = (2.0 / 3.0) * f_pt * n_pts_rank / (bwd_avg_ms * 1e-3) * 1e-12
+    ach_fwd = (1.0 / 3.0) * f_pt * n_pts_rank / (fwd_avg_ms * 1e-3) * 1e-12
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    measured = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+    roofline = {"bound": "fp32", "kernel": "jet_backward_kernel", "achieved": ach_bwd, "peak": peak.value, "unit": "TFLOP/s",
+                "frac": ach_bwd / peak.value, "traffic": None,
+                "peak_source": "scalar-FFMA probe run in this process (tde_fp32_peak_probe); MEASURED_PEAKS.json has "
+                               "only HBM and bf16-tensor peaks and this kernel is FP32-FFMA bound",
+                "launch_ms": bwd_avg_ms, "share_of_step": bwd_ms.value / ms_total,
+                "forward_kernel": {"achieved": ach_fwd, "frac": ach_fwd / peak.value, "launch_ms": fwd_avg_ms,
+                                   "share_of_step": fwd_ms.value / ms_total},
+                "step_flops_frac_of_peak": f_pt * n_pts_rank * args.steps / (ms_total * 1e-3) * 1e-12 / peak.value,
+                "hbm_gbs_measured": measured.get("hbm_gbs"), "bf16_tflops_measured": measured.get("bf16_tflops")}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        nb = max(1, args.cpu_sample // 64)
+        npts, times, cores = cpu_reference_steps(args.workload, args.cpu_sample, nb, 3, 1)
+        cpu_baseline = {"value": npts / statistics.median(times), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_sample} collocation + {nb} pts per boundary group, median of 3 steps after 1 warm-up"}
+
+    h2d = sum(x.numel() * 4 for x in host_groups.values())
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "points_per_gpu": n_col, "boundary_points_per_group_per_gpu": n_bnd,
+                       "points_per_step_job": n_pts_job, "parallelism": f"dp{world} over collocation points, 1 NCCL all-reduce of the flat gradient",
+                       "optimizer": "torch.optim.Adam lr=1e-3",
+                       "l2": "per-step working set (activation stash %.1f GB + %.0f MB partial gradients) is far larger than the 126 MB L2"
+                             % (runner.plan(n_pts_rank).stash_bytes / 1e9, runner.plan(n_pts_rank).workspace_bytes / 1e6)},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

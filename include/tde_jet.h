@@ -157,6 +157,12 @@ int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t 
 int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
 
+/* Instrumentation for bench.py: kernels launched by this library since load, and CUDA-event timing of the
+ * two main kernels (events are recorded on the launching stream right around the kernel, nothing else). */
+long long tde_launch_count(void);
+int tde_profile_begin(void);
+int tde_profile_end(double* forward_ms_total, int32_t* n_forward, double* backward_ms_total, int32_t* n_backward);
+
 /* Measures the sustained scalar-FFMA rate of this GPU (TFLOP/s); the FFMA kernels' roofline denominator. */
 int tde_fp32_peak_probe(double* tflops, void* stream);
 

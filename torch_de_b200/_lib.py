@@ -47,7 +47,8 @@ class TdeLossProgram(C.Structure):
 
 
 EXPORTS = ["tde_last_error", "tde_version", "tde_plan", "tde_jet_forward", "tde_jet_backward",
-           "tde_residual_loss", "tde_adam_step", "tde_fp32_peak_probe"]
+           "tde_residual_loss", "tde_adam_step", "tde_fp32_peak_probe", "tde_launch_count", "tde_profile_begin",
+           "tde_profile_end"]
 
 _LIB = None
 
@@ -63,8 +64,12 @@ def _declare(lib):
     lib.tde_residual_loss.argtypes = [C.POINTER(TdeLossProgram), vp, i64, i32, vp, i64, i64, i64, f32, vp, vp, vp, vp]
     lib.tde_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]
     lib.tde_fp32_peak_probe.argtypes = [C.POINTER(C.c_double), vp]
+    lib.tde_profile_begin.argtypes = []
+    lib.tde_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     for name in EXPORTS[2:]:
         getattr(lib, name).restype = C.c_int
+    lib.tde_launch_count.restype = C.c_longlong
+    lib.tde_launch_count.argtypes = []
     return lib
 
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "jet_launch.h"
 
@@ -29,6 +30,36 @@ int fail(const char* fmt, ...) {
     } while (0)
 
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in per CTA on sm_100
+
+// ---- instrumentation: launch counter and per-kernel CUDA-event timing (bench.py roofline) ----
+long long g_launches = 0;
+bool g_profiling = false;
+struct TimedLaunch {
+    cudaEvent_t e0, e1;
+    int kind;  // 0 forward, 1 backward
+};
+std::vector<TimedLaunch> g_timed;
+
+struct ScopedTimer {
+    cudaStream_t st;
+    int kind;
+    bool on;
+    TimedLaunch t;
+    ScopedTimer(cudaStream_t s, int k) : st(s), kind(k), on(g_profiling) {
+        if (on) {
+            cudaEventCreate(&t.e0);
+            cudaEventCreate(&t.e1);
+            t.kind = kind;
+            cudaEventRecord(t.e0, st);
+        }
+    }
+    ~ScopedTimer() {
+        if (on) {
+            cudaEventRecord(t.e1, st);
+            g_timed.push_back(t);
+        }
+    }
+};
 
 struct Dispatch {
     int nf, smask;
@@ -270,6 +301,7 @@ int launch_pack(const TdeNet* net, const Geometry& g, float* ws, bool want_wt, b
     const int threads = 256;
     const int blocks = (int)std::min<int64_t>((g.packed_floats + threads - 1) / threads, 148 * 8);
     pack_weights_kernel<<<blocks, threads, 0, st>>>(a, ws);
+    ++g_launches;
     TDE_CUDA(cudaGetLastError());
     return 0;
 }
@@ -532,7 +564,11 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
     tde::JetParams p;
     fill_params(g, spec, ws, &p);
     p.x = x; p.B = n_points; p.out = out; p.ld_out = ld_out; p.stash = stash; p.n_stages = g.stages_fwd;
-    TDE_CUDA(g.disp->fwd(p, g.n_ctas, g.smem_fwd, st));
+    {
+        ScopedTimer timer(st, 0);
+        TDE_CUDA(g.disp->fwd(p, g.n_ctas, g.smem_fwd, st));
+    }
+    ++g_launches;
     return 0;
 }
 
@@ -551,7 +587,11 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
     fill_params(g, spec, ws, &p);
     p.x = x; p.B = n_points; p.stash = const_cast<float*>(stash); p.seeds = seeds; p.ld_seeds = ld_seeds;
     p.n_stages = g.stages_bwd;
-    TDE_CUDA(g.disp->bwd(p, g.n_ctas, g.smem_bwd, st));
+    {
+        ScopedTimer timer(st, 1);
+        TDE_CUDA(g.disp->bwd(p, g.n_ctas, g.smem_bwd, st));
+    }
+    g_launches += 2;  // reverse sweep + second-stage reduction
     ReduceArgs r{};
     r.n_layers = net->n_layers; r.W = g.W; r.width = g.width; r.d_in = g.d_in; r.n_out = g.n_out;
     r.rsplit = g.rsplit; r.n_active = g.n_ctas; r.n_params = g.n_params; r.gp_stride = g.gp_stride;
@@ -580,6 +620,7 @@ int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t 
     const int blocks = (int)std::min<int64_t>((n + kLossThreads - 1) / kLossThreads, kLossBlocks);
     residual_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(*prog, streams, ld, n_stream_rows, aux, ld_aux,
                                                                              p0, n, inv_count, row_sums, seeds, point_res);
+    ++g_launches;
     TDE_CUDA(cudaGetLastError());
     return 0;
 }
@@ -594,7 +635,41 @@ int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
     const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 8);
     adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                               (float)bc1, (float)sqrt(bc2));
+    ++g_launches;
     TDE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+long long tde_launch_count(void) { return g_launches; }
+
+int tde_profile_begin(void) {
+    for (auto& t : g_timed) {
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    g_timed.clear();
+    g_profiling = true;
+    return 0;
+}
+
+int tde_profile_end(double* fwd_ms, int32_t* n_fwd, double* bwd_ms, int32_t* n_bwd) {
+    g_profiling = false;
+    double ms[2] = {0.0, 0.0};
+    int cnt[2] = {0, 0};
+    for (auto& t : g_timed) {
+        TDE_CUDA(cudaEventSynchronize(t.e1));
+        float m = 0.f;
+        TDE_CUDA(cudaEventElapsedTime(&m, t.e0, t.e1));
+        ms[t.kind] += m;
+        cnt[t.kind]++;
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    g_timed.clear();
+    if (fwd_ms) *fwd_ms = ms[0];
+    if (n_fwd) *n_fwd = cnt[0];
+    if (bwd_ms) *bwd_ms = ms[1];
+    if (n_bwd) *n_bwd = cnt[1];
     return 0;
 }
 
