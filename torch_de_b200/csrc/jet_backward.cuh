@@ -14,15 +14,15 @@
 
 namespace tde {
 
+// Accumulate into the CTA-private gradient slab.  Each address has exactly one writer thread, so a
+// fire-and-forget vector reduction (RED.128: no load latency to wait on) is still order-deterministic.
 __device__ __forceinline__ void rmw4(float* dst, float4 v, bool first) {
-    if (!first) {
-        const float4 o = *reinterpret_cast<const float4*>(dst);
-        v.x += o.x;
-        v.y += o.y;
-        v.z += o.z;
-        v.w += o.w;
+    if (first) {
+        *reinterpret_cast<float4*>(dst) = v;
+    } else {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
     }
-    *reinterpret_cast<float4*>(dst) = v;
 }
 __device__ __forceinline__ void rmw1(float* dst, float v, bool first) { *dst = first ? v : (*dst + v); }
 
@@ -96,18 +96,21 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         // ===== producer: stream W_l rows (n-major) for the dX GEMM of every hidden layer =====
         if (tid == kComputeThreads) {
-            uint32_t it = 0, go_phase = 0;
+            int s = 0;
+            uint32_t ph = 0, go_phase = 0;
             for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 for (int l = p.L - 1; l >= 1; --l) {
-                    mbar_wait(go, go_phase);  // the dW phase has released the aliased buffer
+                    mbar_wait_backoff(go, go_phase);  // the dW phase has released the aliased buffer
                     go_phase ^= 1;
                     const float* src = p.wn_hidden + (size_t)(l - 1) * W * W;
-                    for (int kc = 0; kc < n_chunks; ++kc, ++it) {
-                        const int s = it % n_stages;
-                        const uint32_t ph = (it / n_stages) & 1;
-                        mbar_wait(&empty[s], ph ^ 1);
+                    for (int kc = 0; kc < n_chunks; ++kc) {
+                        mbar_wait_backoff(&empty[s], ph ^ 1);
                         mbar_expect_tx(&full[s], chunk_bytes);
                         bulk_g2s(ubuf + (size_t)s * kKC * W, src + (size_t)kc * kKC * W, chunk_bytes, &full[s]);
+                        if (++s == n_stages) {
+                            s = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
             }
@@ -138,7 +141,8 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
     float* gp = p.gpart + (size_t)blockIdx.x * p.gp_stride;
     const size_t stash_layer_stride = (size_t)p.n_tiles * W * TPJ;
 
-    uint32_t it = 0;
+    int cs = 0;        // consumer position in the stage ring
+    uint32_t cph = 0;  // and its phase
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const bool first = (tile == (int64_t)blockIdx.x);
         const int64_t pbase = tile * TP;
@@ -290,13 +294,16 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
             for (int pc = 0; pc < PJ; ++pc)
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) acc[pc][j] = 0.0f;
-            for (int kc = 0; kc < n_chunks; ++kc, ++it) {
-                const int s = it % n_stages;
-                const uint32_t ph = (it / n_stages) & 1;
-                mbar_wait(&full[s], ph);
+            for (int kc = 0; kc < n_chunks; ++kc) {
+                const int s = cs;
+                mbar_wait(&full[s], cph);
                 gemm_chunk<PJ>(acc, A + (size_t)(kc * kKC) * pitch + col0, ubuf + (size_t)s * kKC * W, pitch, W, g);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
+                if (++cs == n_stages) {
+                    cs = 0;
+                    cph ^= 1;
+                }
             }
             compute_sync();  // all reads of Hbar_l done; A can be overwritten
 

@@ -10,7 +10,7 @@ namespace tde {
 constexpr int kComputeThreads = 256;            // 8 compute warps
 constexpr int kThreads = kComputeThreads + 128;  // + 1 producer warpgroup (bulk-async weight streamer; donates registers)
 constexpr int kNT = 8;                          // neurons per thread in the GEMM phases
-constexpr int kKC = 8;                          // reduction rows per streamed weight chunk
+constexpr int kKC = 16;                         // reduction rows per streamed weight chunk
 constexpr int kMaxStages = 4;
 
 // ---------------------------------------------------------------------------------------------
@@ -52,6 +52,28 @@ __host__ __device__ constexpr int pair_b_of(int nf, int idx) {
     return a + idx;
 }
 
+struct PairTables {
+    int a[TDE_MAX_SECOND], b[TDE_MAX_SECOND];
+};
+__host__ __device__ constexpr PairTables make_pair_tables(int nf, int mask) {
+    PairTables t{};
+    int q = 0;
+    for (int idx = 0; idx < 6 && q < TDE_MAX_SECOND; ++idx)
+        if (mask >> idx & 1) {
+            t.a[q] = pair_a_of(nf > 0 ? nf : 1, idx);
+            t.b[q] = pair_b_of(nf > 0 ? nf : 1, idx);
+            ++q;
+        }
+    return t;
+}
+
+template <int Q, int NF, int SMASK>
+struct PairAt {
+    static constexpr int idx = nth_set_bit(SMASK, Q);
+    static constexpr int a = pair_a_of(NF, idx);
+    static constexpr int b = pair_b_of(NF, idx);
+};
+
 template <int NF_, int SMASK_>
 struct JetSpecT {
     static constexpr int NF = NF_;
@@ -62,9 +84,16 @@ struct JetSpecT {
     static constexpr int PJ = PT * J;            // jet columns per thread (multiple of 4)
     static constexpr int NV = PJ / 4;
     static_assert(PJ % 4 == 0, "thread jet columns must vectorise to float4");
-    __host__ __device__ static constexpr int pa(int q) { return pair_a_of(NF_, nth_set_bit(SMASK_, q)); }
-    __host__ __device__ static constexpr int pb(int q) { return pair_b_of(NF_, nth_set_bit(SMASK_, q)); }
 };
+
+// compile-time loop over the second-order pairs: f(integral_constant<q>, integral_constant<a>, integral_constant<b>)
+template <class S, int Q = 0, class F>
+__device__ __forceinline__ void for_each_pair(F&& f) {
+    if constexpr (Q < S::NS) {
+        f(Q, PairAt<Q, S::NF, S::SMASK>::a, PairAt<Q, S::NF, S::SMASK>::b);
+        for_each_pair<S, Q + 1>(f);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Kernel parameter block (passed by value, __grid_constant__)
@@ -144,6 +173,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// producer-side wait: long hardware suspend + nanosleep back-off (one thread; must not burn issue slots)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
@@ -208,9 +254,9 @@ __device__ __forceinline__ void act_forward(int act, float (&h)[S::J], float (&z
     z[0] = s.s0;
 #pragma unroll
     for (int a = 0; a < S::NF; ++a) z[1 + a] = s.s1 * h[1 + a];
-#pragma unroll
-    for (int q = 0; q < S::NS; ++q)
-        z[1 + S::NF + q] = fmaf(s.s2 * h[1 + S::pa(q)], h[1 + S::pb(q)], s.s1 * h[1 + S::NF + q]);
+    for_each_pair<S>([&](const int q, const int a, const int b) {
+        z[1 + S::NF + q] = fmaf(s.s2 * h[1 + a], h[1 + b], s.s1 * h[1 + S::NF + q]);
+    });
     h[0] = st0;
 }
 
@@ -221,9 +267,9 @@ __device__ __forceinline__ void act_recompute(int act, const float (&st)[S::J], 
     z[0] = s.s0;
 #pragma unroll
     for (int a = 0; a < S::NF; ++a) z[1 + a] = s.s1 * st[1 + a];
-#pragma unroll
-    for (int q = 0; q < S::NS; ++q)
-        z[1 + S::NF + q] = fmaf(s.s2 * st[1 + S::pa(q)], st[1 + S::pb(q)], s.s1 * st[1 + S::NF + q]);
+    for_each_pair<S>([&](const int q, const int a, const int b) {
+        z[1 + S::NF + q] = fmaf(s.s2 * st[1 + a], st[1 + b], s.s1 * st[1 + S::NF + q]);
+    });
 }
 
 // adjoint: given zb = dL/dz (jet) and the stash (st0, h_c) produce hb = dL/dh (jet), optionally z too
@@ -237,23 +283,22 @@ __device__ __forceinline__ void act_backward(int act, const float (&st)[S::J], c
         hb[1 + a] = s.s1 * zb[1 + a];
         h0b = fmaf(s.s2 * st[1 + a], zb[1 + a], h0b);
     }
-#pragma unroll
-    for (int q = 0; q < S::NS; ++q) {
-        const int ia = 1 + S::pa(q), ib = 1 + S::pb(q), iq = 1 + S::NF + q;
+    for_each_pair<S>([&](const int q, const int a, const int b) {
+        const int ia = 1 + a, ib = 1 + b, iq = 1 + S::NF + q;
         const float zq = zb[iq];
         hb[iq] = s.s1 * zq;
         hb[ia] = fmaf(s.s2 * st[ib], zq, hb[ia]);
         hb[ib] = fmaf(s.s2 * st[ia], zq, hb[ib]);
         h0b = fmaf(fmaf(s.s3 * st[ia], st[ib], s.s2 * st[iq]), zq, h0b);
-    }
+    });
     hb[0] = h0b;
     if (WANT_Z) {
         z[0] = s.s0;
 #pragma unroll
         for (int a = 0; a < S::NF; ++a) z[1 + a] = s.s1 * st[1 + a];
-#pragma unroll
-        for (int q = 0; q < S::NS; ++q)
-            z[1 + S::NF + q] = fmaf(s.s2 * st[1 + S::pa(q)], st[1 + S::pb(q)], s.s1 * st[1 + S::NF + q]);
+        for_each_pair<S>([&](const int q, const int a, const int b) {
+            z[1 + S::NF + q] = fmaf(s.s2 * st[1 + a], st[1 + b], s.s1 * st[1 + S::NF + q]);
+        });
     }
 }
 

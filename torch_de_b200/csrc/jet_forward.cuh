@@ -70,16 +70,19 @@ __global__ void __launch_bounds__(kThreads, 1) jet_forward_kernel(const __grid_c
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         // ===== producer warp: stream hidden-layer weight rows through the stage ring =====
         if (tid == kComputeThreads) {
-            uint32_t it = 0;
+            int s = 0;
+            uint32_t ph = 0;
             for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 for (int l = 1; l < p.L; ++l) {
                     const float* src = p.wt_hidden + (size_t)(l - 1) * W * W;
-                    for (int kc = 0; kc < n_chunks; ++kc, ++it) {
-                        const int s = it % n_stages;
-                        const uint32_t ph = (it / n_stages) & 1;
-                        mbar_wait(&empty[s], ph ^ 1);
+                    for (int kc = 0; kc < n_chunks; ++kc) {
+                        mbar_wait_backoff(&empty[s], ph ^ 1);
                         mbar_expect_tx(&full[s], chunk_bytes);
                         bulk_g2s(wbuf + (size_t)s * kKC * W, src + (size_t)kc * kKC * W, chunk_bytes, &full[s]);
+                        if (++s == n_stages) {
+                            s = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
             }
@@ -97,7 +100,8 @@ __global__ void __launch_bounds__(kThreads, 1) jet_forward_kernel(const __grid_c
 
     for (int i = tid; i < p.n_out * W; i += kComputeThreads) wout_s[i] = p.w_out[i];
 
-    uint32_t it = 0;
+    int cs = 0;        // consumer position in the stage ring
+    uint32_t cph = 0;  // and its phase
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int64_t pbase = tile * TP;
         // ---- stage the points of this tile ----
@@ -155,13 +159,16 @@ __global__ void __launch_bounds__(kThreads, 1) jet_forward_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < kNT; ++j) acc[pc][j] = 0.0f;
 
-            for (int kc = 0; kc < n_chunks; ++kc, ++it) {
-                const int s = it % n_stages;
-                const uint32_t ph = (it / n_stages) & 1;
-                mbar_wait(&full[s], ph);
+            for (int kc = 0; kc < n_chunks; ++kc) {
+                const int s = cs;
+                mbar_wait(&full[s], cph);
                 gemm_chunk<PJ>(acc, A + (size_t)(kc * kKC) * pitch + col0, wbuf + (size_t)s * kKC * W, pitch, W, g);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
+                if (++cs == n_stages) {
+                    cs = 0;
+                    cph ^= 1;
+                }
             }
             compute_sync();  // every warp is done reading A for this layer
 
