@@ -248,32 +248,40 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
                 }
                 compute_sync();
                 for (int np = 0; dw_active && np < n_pass; ++np) {
-                    float acc[8][8];
+                    // acc2[j][i] = (partial over even columns, partial over odd columns): operands are natural
+                    // 64-bit pairs of the float4 loads, so the whole product runs on FFMA2 with no packing moves
+                    uint64_t acc2[8][8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[j][i] = 0.0f;
+                        for (int i = 0; i < 8; ++i) acc2[j][i] = 0ull;
                     const float* Hrow = A + (size_t)(np * 8 * NI + ni) * pitch;
                     const float* Zrow = ubuf + (size_t)(8 * ki) * pitch;
                     const int cbeg = rs * cols_per_split, cend = cbeg + cols_per_split;
+#pragma unroll 2
                     for (int c4 = cbeg; c4 < cend; c4 += 4) {
-                        float4 hv[8], zv[8];
+                        ulonglong2 hv[8], zv[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) hv[j] = *reinterpret_cast<const float4*>(Hrow + (size_t)(NI * j) * pitch + c4);
+                        for (int j = 0; j < 8; ++j) hv[j] = *reinterpret_cast<const ulonglong2*>(Hrow + (size_t)(NI * j) * pitch + c4);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) zv[i] = *reinterpret_cast<const float4*>(Zrow + (size_t)i * pitch + c4);
+                        for (int i = 0; i < 8; ++i) zv[i] = *reinterpret_cast<const ulonglong2*>(Zrow + (size_t)i * pitch + c4);
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                float a = acc[j][i];
-                                a = fmaf(hv[j].x, zv[i].x, a);
-                                a = fmaf(hv[j].y, zv[i].y, a);
-                                a = fmaf(hv[j].z, zv[i].z, a);
-                                a = fmaf(hv[j].w, zv[i].w, a);
-                                acc[j][i] = a;
+                                fma2(acc2[j][i], hv[j].x, zv[i].x);
+                                fma2(acc2[j][i], hv[j].y, zv[i].y);
                             }
                     }
+                    float acc[8][8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float lo, hi;
+                            unpack2(acc2[j][i], lo, hi);
+                            acc[j][i] = lo + hi;
+                        }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int n = np * 8 * NI + ni + NI * j;
@@ -289,11 +297,8 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
             if (lane == 0) mbar_arrive(go);
 
             // ---- Zbar_{l-1}[col][k] = sum_n Hbar_l[n][col] * W_l[n][k]  (k = g + NG*j) ----
-            float acc[PJ][kNT];
-#pragma unroll
-            for (int pc = 0; pc < PJ; ++pc)
-#pragma unroll
-                for (int j = 0; j < kNT; ++j) acc[pc][j] = 0.0f;
+            AccTile<PJ> acc;
+            acc.zero();
             for (int kc = 0; kc < n_chunks; ++kc) {
                 const int s = cs;
                 mbar_wait(&full[s], cph);
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
                 for (int pt = 0; pt < PT; ++pt) {
                     float zb[J], zdummy[J];
 #pragma unroll
-                    for (int c = 0; c < J; ++c) zb[c] = acc[pt * J + c][j];
+                    for (int c = 0; c < J; ++c) zb[c] = acc.get(pt * J + c, j);
                     act_backward<S, false>(p.act, st[pt], zb, hb[pt], zdummy);
                 }
                 if (active) store_row_vec_b<S>(A + (size_t)n * pitch + col0, hb);

@@ -307,28 +307,58 @@ __device__ __forceinline__ void act_backward(int act, const float (&st)[S::J], c
 //   acc[pc][j] += sum_k A[k][col0+pc] * Bq[k][q(g,j)]      (A: smem tile, K-major; Bq: streamed chunks)
 // Consumers wait on full[stage], compute kKC reduction rows, release with one arrive per warp.
 // ---------------------------------------------------------------------------------------------
+// packed FP32 pairs (Blackwell fma.rn.f32x2: two FMAs per issue slot and per register-file read)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void fma2(uint64_t& d, uint64_t a, uint64_t b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
+// Accumulator tile of the register GEMM: PJ jet columns x 8 neurons, stored as column PAIRS
+// (columns 2i, 2i+1 share one 64-bit register) so the inner product runs on FFMA2.
 template <int PJ>
-__device__ __forceinline__ void gemm_chunk(float (&acc)[PJ][kNT], const float* __restrict__ Arow,
+struct AccTile {
+    uint64_t v[PJ / 2][kNT];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < PJ / 2; ++i)
+#pragma unroll
+            for (int j = 0; j < kNT; ++j) v[i][j] = 0ull;
+    }
+    __device__ __forceinline__ float get(int pc, int j) const {
+        float lo, hi;
+        unpack2(v[pc >> 1][j], lo, hi);
+        return (pc & 1) ? hi : lo;
+    }
+};
+
+template <int PJ>
+__device__ __forceinline__ void gemm_chunk(AccTile<PJ>& acc, const float* __restrict__ Arow,
                                            const float* __restrict__ wchunk, int pitch, int W, int g) {
     constexpr int NV = PJ / 4;
-#pragma unroll
+#pragma unroll 4
     for (int kk = 0; kk < kKC; ++kk) {
-        float a[PJ];
+        uint64_t a2[PJ / 2];
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-            const float4 t = *reinterpret_cast<const float4*>(Arow + kk * pitch + 4 * v);
-            a[4 * v + 0] = t.x;
-            a[4 * v + 1] = t.y;
-            a[4 * v + 2] = t.z;
-            a[4 * v + 3] = t.w;
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(Arow + kk * pitch + 4 * v);
+            a2[2 * v] = t.x;
+            a2[2 * v + 1] = t.y;
         }
         const float4 w0 = *reinterpret_cast<const float4*>(wchunk + kk * W + 4 * g);
         const float4 w1 = *reinterpret_cast<const float4*>(wchunk + kk * W + (W >> 1) + 4 * g);
-        const float w[kNT] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const uint64_t w2[kNT] = {pack2(w0.x, w0.x), pack2(w0.y, w0.y), pack2(w0.z, w0.z), pack2(w0.w, w0.w),
+                                  pack2(w1.x, w1.x), pack2(w1.y, w1.y), pack2(w1.z, w1.z), pack2(w1.w, w1.w)};
 #pragma unroll
-        for (int pc = 0; pc < PJ; ++pc)
+        for (int i = 0; i < PJ / 2; ++i)
 #pragma unroll
-            for (int j = 0; j < kNT; ++j) acc[pc][j] = fmaf(a[pc], w[j], acc[pc][j]);
+            for (int j = 0; j < kNT; ++j) fma2(acc.v[i][j], a2[i], w2[j]);
     }
 }
 

@@ -153,11 +153,12 @@ __global__ void __launch_bounds__(kThreads, 1) jet_forward_kernel(const __grid_c
 
         // ---- hidden layers ----
         for (int l = 1; l < p.L; ++l) {
-            float acc[PJ][kNT];
+            AccTile<PJ> acc;
+            acc.zero();
+            // bias of this layer for the thread's 8 neurons: fetched now, consumed after the GEMM
+            float bn[kNT];
 #pragma unroll
-            for (int pc = 0; pc < PJ; ++pc)
-#pragma unroll
-                for (int j = 0; j < kNT; ++j) acc[pc][j] = 0.0f;
+            for (int j = 0; j < kNT; ++j) bn[j] = __ldg(p.b_hidden + (size_t)(l - 1) * W + g + NG * j);
 
             for (int kc = 0; kc < n_chunks; ++kc) {
                 const int s = cs;
@@ -172,19 +173,17 @@ __global__ void __launch_bounds__(kThreads, 1) jet_forward_kernel(const __grid_c
             }
             compute_sync();  // every warp is done reading A for this layer
 
-            const float* bias = p.b_hidden + (size_t)(l - 1) * W;
             float* stash_l = stash_tile ? stash_tile + (size_t)l * stash_layer_stride : nullptr;
 #pragma unroll
             for (int j = 0; j < kNT; ++j) {
                 const int n = g + NG * j;
-                const float bn = __ldg(bias + n);
                 float zt[PT][J], st[PT][J];
 #pragma unroll
                 for (int pt = 0; pt < PT; ++pt) {
                     float h[J];
 #pragma unroll
-                    for (int c = 0; c < J; ++c) h[c] = acc[pt * J + c][j];
-                    h[0] += bn;
+                    for (int c = 0; c < J; ++c) h[c] = acc.get(pt * J + c, j);
+                    h[0] += bn[j];
                     act_forward<S>(p.act, h, zt[pt]);
 #pragma unroll
                     for (int c = 0; c < J; ++c) st[pt][c] = h[c];
