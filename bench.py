@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--points-per-gpu", type=int, default=0)
     ap.add_argument("--boundary-per-gpu", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=4096, help="collocation points per CPU-baseline step")
+    ap.add_argument("--gpu-ref-sample", type=int, default=16384, help="collocation points per GPU-reference micro-batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -122,6 +123,35 @@ def cpu_reference_steps(workload, n_col, n_bnd, steps, warmup):
         if i >= warmup:
             times.append(dt)
     return n_pts, times, cores
+
+
+def gpu_reference_steps(workload, n_col, n_bnd, steps, warmup, dev):
+    """The reference's own algorithm (oracle port: torch.func vmap(jacrev(jacrev)) + autograd + Adam) on the SAME
+    GPU, micro-batched: the denominator of the north star's >=20x target."""
+    from oracle import ref_autograd as O
+    owl = O.WORKLOADS[workload]()
+    n = owl.net
+    params = [p.to(dev).requires_grad_(True) for p in O.init_mlp_params(n["d_in"], n["n_out"], n["width"], n["n_act"], seed=1234)]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    groups = {g: x.to(dev) for g, x in O.sample_groups(owl, n_col, n_bnd, seed=1234).items()}
+    n_pts = sum(x.shape[0] for x in groups.values())
+
+    def one():
+        res = O.step(owl, params, groups)
+        for p, g in zip(params, res["grads"]):
+            p.grad = g
+        opt.step()
+        opt.zero_grad()
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return n_pts * steps / (e0.elapsed_time(e1) * 1e-3), n_pts
 
 
 def run_reference(args, rank):
@@ -262,6 +292,17 @@ def run_ours(args, rank, local_rank, world):
         cpu_baseline = {"value": npts / statistics.median(times), "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{args.cpu_sample} collocation + {nb} pts per boundary group, median of 3 steps after 1 warm-up"}
 
+    reference_gpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        del batch, dev_groups
+        torch.cuda.empty_cache()
+        try:
+            v, npts = gpu_reference_steps(args.workload, args.gpu_ref_sample, max(1, args.gpu_ref_sample // 64), 3, 2, dev)
+            reference_gpu = {"value": v, "unit": UNIT, "kind": "port", "device": torch.cuda.get_device_name(dev),
+                             "sample": f"{npts} points per micro-batch step, 3 timed steps after 2 warm-ups (torch.func + autograd + Adam)"}
+        except Exception as exc:  # noqa: BLE001 - informational leg only
+            reference_gpu = {"unavailable": repr(exc)[:200]}
+
     h2d = sum(x.numel() * 4 for x in host_groups.values())
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -274,7 +315,8 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "reference_gpu": reference_gpu}
     print(json.dumps(line), flush=True)
 
 
