@@ -87,6 +87,8 @@ typedef struct TdePlan {
 
 const char* tde_last_error(void);
 int tde_version(void);
+/* sizeof of the ABI structs as compiled (0 TdeNet, 1 TdeJetSpec, 2 TdePlan, 3 TdeLossProgram): bindings verify at load. */
+int tde_abi_struct_bytes(int which);
 
 /* Validates (net, spec) and reports buffer sizes for a batch of n_points. Host-only, no launch. */
 int tde_plan(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points, TdePlan* plan);
@@ -122,8 +124,8 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
 #define TDE_OP_SIN 9
 #define TDE_OP_COS 10
 #define TDE_OP_DIV 11
-#define TDE_MAX_REGS 48
-#define TDE_MAX_OPS 96
+#define TDE_MAX_REGS 64
+#define TDE_MAX_OPS 128
 #define TDE_MAX_ROWS 8
 
 typedef struct TdeOp {
@@ -145,13 +147,16 @@ typedef struct TdeLossProgram {
 
 /*
  * streams[(row)*ld + p] for p in [p0, p0+n) (row indexing as `out` above), aux[(row)*ld_aux + p - p0].
- * row_sums[n_rows] += sum_p w*|res|^2 * inv_count   (un-weighted by coef; caller recombines)
- * seeds[(row)*ld + p] = coef_r * inv_count * d(w*res^2)/d(stream)   (overwrites the [p0,p0+n) slice;
- * rows never loaded get zeros).  point_res (optional) [n_rows][n]: per-point residuals (R3 sampler).
+ * Any of the three outputs may be NULL:
+ *   row_sums[n_rows] += inv_count * sum_p w*|res|^2          (un-weighted by coef; caller recombines)
+ *   seeds[(row)*ld + p] = sum_r coef_r * inv_count * d(w*res_r^2)/d(stream)   (overwrites the [p0,p0+n) slice of
+ *                         every stream row; rows never loaded get zeros); coef_r = prog.coef[r] * coef_dev[r]
+ *                         (coef_dev: optional DEVICE array = d total / d row, so no host sync is needed)
+ *   point_res[n_rows][n]: per-point residuals (what utils/sampling.py:R3_sampler consumes).
  */
 int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
                       const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
-                      float* row_sums, float* seeds, float* point_res, void* stream);
+                      const float* coef_dev, float* row_sums, float* seeds, float* point_res, void* stream);
 
 /* Adam (torch.optim.Adam defaults semantics: bias-corrected, eps outside sqrt of v_hat), one launch. */
 int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,

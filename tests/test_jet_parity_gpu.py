@@ -105,3 +105,124 @@ def test_repeatable_bitwise():
     b = run_product('ldc_small')[-1]
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize('fixture', ['spring', 'burgers', 'allen_cahn', 'ldc_small'])
+def test_fused_loss_kernel_matches_torch_path(fixture):
+    """tde_residual_loss (rows + seeds) against the torch elementwise evaluation of the same loss table."""
+    z, owl, params, groups = load(fixture)
+    wl = product_workload(fixture)
+    results = {}
+    for fused in (True, False):
+        net, lins = load_net(wl, params, 'cuda')
+        pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+        batch = T.make_batch(wl.input_vars, {g: x.cuda() for g, x in groups.items()})
+        out = pinn.calculate(batch)
+        handler = wl.build_losses(list(groups.keys()))
+        handler.fused = fused
+        loss = handler(batch, out)
+        total = wl.combine(loss.grouped_losses('loss_type'))
+        total.backward()
+        if fused:
+            assert set(handler.fusion_report.values()) == {'fused'}, handler.fusion_report
+            assert all(r['residual'] is None for r in loss.losses)
+        results[fused] = (loss.individual_losses().detach().cpu(), float(total),
+                          torch.cat([p.grad.flatten().cpu() for lin in lins for p in (lin.weight, lin.bias)]))
+    rows_f, tot_f, g_f = results[True]
+    rows_t, tot_t, g_t = results[False]
+    assert torch.allclose(rows_f, rows_t, rtol=2e-5, atol=1e-12)
+    assert abs(tot_f - tot_t) <= 2e-5 * abs(tot_t)
+    assert rel_l2(g_f, g_t) < 2e-5
+
+
+def test_unfusable_row_falls_back_to_torch_ops_for_its_group_only():
+    z, owl, params, groups = load('burgers')
+    wl = product_workload('burgers')
+    net, lins = load_net(wl, params, 'cuda')
+    pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+    batch = T.make_batch(wl.input_vars, {g: x.cuda() for g, x in groups.items()})
+    out = pinn.calculate(batch)
+    handler = wl.build_losses(list(groups.keys()))
+    handler.add_residual('collocation points', {'exp_term': T.DE_func(lambda u, **kw: torch.exp(u) - 1)})
+    loss = handler(batch, out)
+    assert handler.fusion_report['collocation points'].startswith('torch path')
+    assert handler.fusion_report['x0'] == 'fused'
+    ref = wl.build_losses(list(groups.keys()))
+    ref.add_residual('collocation points', {'exp_term': T.DE_func(lambda u, **kw: torch.exp(u) - 1)})
+    ref.fused = False
+    assert torch.allclose(loss.individual_losses(), ref(batch, out).individual_losses(), rtol=2e-5)
+    loss.sum().backward()
+
+
+def test_target_groups_value_only_for_other_groups():
+    z, owl, params, groups = load('ldc_small')
+    wl = product_workload('ldc_small')
+    net, lins = load_net(wl, params, 'cuda')
+    pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+    batch = T.make_batch(wl.input_vars, {g: x.cuda() for g, x in groups.items()})
+    full = pinn.calculate(batch)
+    part = pinn.calculate(batch, target_groups='collocation points')
+    assert set(part['inlet'].keys()) == {'u', 'v', 'p'}                       # base.py:41-54 semantics
+    assert set(part['collocation points'].keys()) == set(pinn.derivatives)
+    for k in ('u', 'v', 'p'):
+        assert torch.allclose(part['inlet'][k], full['inlet'][k], rtol=1e-6, atol=1e-7)
+    for k in pinn.derivatives:
+        assert torch.allclose(part['collocation points'][k], full['collocation points'][k], rtol=1e-6, atol=1e-6)
+    (part['inlet']['u'].sum() + part['collocation points']['u_xx'].sum()).backward()
+    assert all(p.grad is not None for p in net.parameters())
+
+
+def test_sin_activation_and_plain_tensor_input():
+    from oracle import ref_autograd as O
+    params = O.init_mlp_params(2, 1, 64, 3, seed=5)
+    net = T.MLP(2, 1, 64, 2, activation='sin')
+    lins, _ = T.extract_layers(net)
+    with torch.no_grad():
+        for i, lin in enumerate(lins):
+            lin.weight.copy_(params[2 * i]); lin.bias.copy_(params[2 * i + 1])
+    net = net.cuda()
+    pinn = T.DE_Getter(net, ['x', 't'], ['u'], ['u_xt', 'u_tt'])
+    x = torch.rand(77, 2, generator=torch.Generator().manual_seed(3))
+    out = pinn(x.cuda())['all']
+    imap = O.derivative_index_map(['x', 't'], ['u'], ['u_xt', 'u_tt'])
+    ref = O.streams([p.double() for p in params], x.double(), imap, 'sin')
+    for k in imap:
+        assert rel_l2(out[k].detach().cpu(), ref[k]) < TOL_STREAM, k
+    loss = sum(v.pow(2).mean() for v in out.values())
+    loss.backward()
+    pr = [p.double().requires_grad_(True) for p in params]
+    rref = O.streams(pr, x.double(), imap, 'sin')
+    gref = torch.autograd.grad(sum(v.pow(2).mean() for v in rref.values()), pr)
+    got = torch.cat([p.grad.flatten().cpu() for lin in lins for p in (lin.weight, lin.bias)])
+    assert rel_l2(got, torch.cat([g.flatten() for g in gref])) < TOL_LOSS
+
+
+def test_retain_graph_multiple_backwards_like_gradnorm():
+    """utils/Loss_weighting.py:39: k x autograd.grad(loss_k, params, retain_graph=True, allow_unused=True) on one forward."""
+    z, owl, params, groups = load('ldc_small')
+    wl = product_workload('ldc_small')
+    net, lins = load_net(wl, params, 'cuda')
+    pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+    batch = T.make_batch(wl.input_vars, {g: x.cuda() for g, x in groups.items()})
+    out = pinn.calculate(batch)
+    loss = wl.build_losses(list(groups.keys()))(batch, out)
+    rows = loss.individual_losses()
+    ps = list(net.parameters())
+    per_row = [torch.autograd.grad(r, ps, retain_graph=True, allow_unused=True) for r in rows]
+    total = torch.autograd.grad(rows.sum(), ps)
+    for i, g in enumerate(total):
+        acc = sum(pr[i] for pr in per_row)
+        assert rel_l2(acc.cpu(), g.cpu()) < 1e-5
+
+
+def test_empty_and_ragged_batches():
+    net = T.MLP(2, 1, 64, 2).cuda()
+    pinn = T.DE_Getter(net, ['x', 't'], ['u'], ['u_x', 'u_xx'])
+    out = pinn(torch.zeros(0, 2, device='cuda'))['all']
+    assert out['u_xx'].shape == (0,)
+    for n in (1, 31, 97, 129):                  # not multiples of the tile size
+        x = torch.rand(n, 2, device='cuda')
+        o = pinn(x)['all']
+        assert o['u'].shape == (n,)
+        assert torch.allclose(o['u'], net(x)[:, 0], rtol=1e-5, atol=1e-6)
+        o['u_xx'].sum().backward()

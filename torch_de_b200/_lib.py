@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libtde_jet.so")
 
 ACT_NONE, ACT_TANH, ACT_SIN = 0, 1, 2
 MAX_LAYERS, MAX_IN, MAX_OUT, MAX_FIRST, MAX_SECOND = 24, 8, 4, 3, 6
-MAX_REGS, MAX_OPS, MAX_ROWS = 48, 96, 8
+MAX_REGS, MAX_OPS, MAX_ROWS = 64, 128, 8
 (OP_CONST, OP_LOAD, OP_AUX, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_POWI, OP_ABS, OP_SIN, OP_COS, OP_DIV) = range(12)
 
 
@@ -46,7 +46,7 @@ class TdeLossProgram(C.Structure):
                 ("w_const", C.c_float * MAX_ROWS), ("coef", C.c_float * MAX_ROWS)]
 
 
-EXPORTS = ["tde_last_error", "tde_version", "tde_plan", "tde_jet_forward", "tde_jet_backward",
+EXPORTS = ["tde_last_error", "tde_version", "tde_abi_struct_bytes", "tde_plan", "tde_jet_forward", "tde_jet_backward",
            "tde_residual_loss", "tde_adam_step", "tde_fp32_peak_probe", "tde_launch_count", "tde_profile_begin",
            "tde_profile_end"]
 
@@ -61,12 +61,12 @@ def _declare(lib):
     lib.tde_plan.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), i64, C.POINTER(TdePlan)]
     lib.tde_jet_forward.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), vp, i64, vp, i64, vp, vp, vp]
     lib.tde_jet_backward.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), vp, i64, vp, vp, i64, f32, vp, vp, vp]
-    lib.tde_residual_loss.argtypes = [C.POINTER(TdeLossProgram), vp, i64, i32, vp, i64, i64, i64, f32, vp, vp, vp, vp]
+    lib.tde_residual_loss.argtypes = [C.POINTER(TdeLossProgram), vp, i64, i32, vp, i64, i64, i64, f32, vp, vp, vp, vp, vp]
     lib.tde_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]
     lib.tde_fp32_peak_probe.argtypes = [C.POINTER(C.c_double), vp]
     lib.tde_profile_begin.argtypes = []
     lib.tde_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
-    for name in EXPORTS[2:]:
+    for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
     lib.tde_launch_count.restype = C.c_longlong
     lib.tde_launch_count.argtypes = []
@@ -80,7 +80,14 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(torch_de_b200 has no CPU or eager fallback)")
-        _LIB = _declare(C.CDLL(LIB_PATH))
+        handle = _declare(C.CDLL(LIB_PATH))
+        handle.tde_abi_struct_bytes.argtypes = [C.c_int]
+        handle.tde_abi_struct_bytes.restype = C.c_int
+        for i, st in enumerate((TdeNet, TdeJetSpec, TdePlan, TdeLossProgram)):
+            if handle.tde_abi_struct_bytes(i) != C.sizeof(st):
+                raise RuntimeError(f"{LIB_PATH} was built from a different include/tde_jet.h ({st.__name__}: "
+                                   f"{handle.tde_abi_struct_bytes(i)} vs {C.sizeof(st)} bytes): rebuild it")
+        _LIB = handle
     return _LIB
 
 

@@ -389,12 +389,16 @@ __device__ unsigned int g_loss_ticket = 0;
 __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
     const __grid_constant__ TdeLossProgram prog, const float* __restrict__ streams, int64_t ld, int n_stream_rows,
     const float* __restrict__ aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
-    float* __restrict__ row_sums, float* __restrict__ seeds, float* __restrict__ point_res) {
+    const float* __restrict__ coef_dev, float* __restrict__ row_sums, float* __restrict__ seeds,
+    float* __restrict__ point_res) {
     __shared__ float red[TDE_MAX_ROWS][kLossThreads / 32];
     __shared__ bool is_last;
-    float part[TDE_MAX_ROWS];
+    float part[TDE_MAX_ROWS], coef[TDE_MAX_ROWS];
 #pragma unroll
-    for (int r = 0; r < TDE_MAX_ROWS; ++r) part[r] = 0.0f;
+    for (int r = 0; r < TDE_MAX_ROWS; ++r) {
+        part[r] = 0.0f;
+        coef[r] = r < prog.n_rows ? prog.coef[r] * (coef_dev ? coef_dev[r] : 1.0f) : 0.0f;
+    }
 
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = p0 + i;
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
             const float res = v[prog.res_reg[r]];
             const float w = prog.w_aux[r] >= 0 ? aux[(int64_t)prog.w_aux[r] * ld_aux + i] : prog.w_const[r];
             part[r] += w * res * res;
-            adj[prog.res_reg[r]] += prog.coef[r] * inv_count * 2.0f * w * res;
+            adj[prog.res_reg[r]] += coef[r] * inv_count * 2.0f * w * res;
             if (point_res) point_res[(int64_t)r * n + i] = res;
         }
         if (seeds) {
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
     __syncthreads();
     if (is_last) {
         __threadfence();
-        if (threadIdx.x < prog.n_rows) {
+        if (threadIdx.x < prog.n_rows && row_sums) {
             float s = 0.0f;
             for (unsigned b = 0; b < gridDim.x; ++b) s += g_loss_partials[b * TDE_MAX_ROWS + threadIdx.x];
             row_sums[threadIdx.x] += s * inv_count;
@@ -532,7 +536,17 @@ __global__ void __launch_bounds__(512) ffma_probe_kernel(float* out, int iters, 
 extern "C" {
 
 const char* tde_last_error(void) { return g_err.c_str(); }
-int tde_version(void) { return 100; }
+int tde_version(void) { return 101; }
+
+int tde_abi_struct_bytes(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(TdeNet);
+        case 1: return (int)sizeof(TdeJetSpec);
+        case 2: return (int)sizeof(TdePlan);
+        case 3: return (int)sizeof(TdeLossProgram);
+        default: return -1;
+    }
+}
 
 int tde_plan(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points, TdePlan* plan) {
     if (!plan) return fail("null plan");
@@ -604,9 +618,10 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
 }
 
 int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
-                      const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count, float* row_sums,
-                      float* seeds, float* point_res, void* stream) {
-    if (!prog || !streams || !row_sums) return fail("null program/streams/row_sums");
+                      const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
+                      const float* coef_dev, float* row_sums, float* seeds, float* point_res, void* stream) {
+    if (!prog || !streams) return fail("null program/streams");
+    if (!row_sums && !seeds && !point_res) return fail("nothing to compute: row_sums, seeds and point_res are all null");
     if (prog->n_ops < 1 || prog->n_ops > TDE_MAX_OPS) return fail("n_ops %d out of range", prog->n_ops);
     if (prog->n_rows < 1 || prog->n_rows > TDE_MAX_ROWS) return fail("n_rows %d out of range", prog->n_rows);
     for (int k = 0; k < prog->n_ops; ++k) {
@@ -619,7 +634,7 @@ int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t 
     if (n == 0) return 0;
     const int blocks = (int)std::min<int64_t>((n + kLossThreads - 1) / kLossThreads, kLossBlocks);
     residual_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(*prog, streams, ld, n_stream_rows, aux, ld_aux,
-                                                                             p0, n, inv_count, row_sums, seeds, point_res);
+                                                                             p0, n, inv_count, coef_dev, row_sums, seeds, point_res);
     ++g_launches;
     TDE_CUDA(cudaGetLastError());
     return 0;

@@ -159,6 +159,14 @@ class _JetFunction(torch.autograd.Function):
         return (None, None, *runner.split_flat(flat))
 
 
+class JetOutput(dict):
+    """The engine's result dict ({'all': {...}, group: {...}}) plus the raw stream block it views, so the loss
+    side can run the fused residual kernel on it: `block[J*n_out, B]`, `stream_row[name]`, `ranges[group]`."""
+    block: torch.Tensor = None
+    stream_row: Dict[str, int] = None
+    ranges: Dict[str, tuple] = None
+
+
 def _group_name(key, group):
     return getattr(group, 'name', key)
 
@@ -201,10 +209,14 @@ class Jet_engine(_EngineBase):
         x, names, sizes = self._cat_groups(groups)
         block = self._jets(self._full, x)
         keys = list(self.derivatives.keys())
-        out = {'all': self._named(self._full, block, keys)}
+        out = JetOutput({'all': self._named(self._full, block, keys)})
+        out.block = block
+        out.stream_row = {k: self._full.ch.row(k) for k in keys}
+        out.ranges = {}
         lo = 0
         for name, n in zip(names, sizes):
             out[name] = self._named(self._full, block, keys, lo, lo + n)
+            out.ranges[name] = (lo, lo + n)
             lo += n
         return out
 

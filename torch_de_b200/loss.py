@@ -11,6 +11,7 @@ import torch
 from torch import Tensor
 
 from .equations import DE_func
+from . import fused_loss as FL
 
 
 class GroupedLosses(dict):
@@ -33,6 +34,9 @@ class Loss:
 
     def point_error(self) -> List[Tensor]:
         for row in self.losses:
+            if row.get('residual') is None:
+                raise RuntimeError("per-point residuals are not materialised by the fused loss kernel; "
+                                   "call Loss_handler.calculate(..., fused=False) when they are needed")
             if row.get('point_error') is None:
                 row['point_error'] = self.error_func(row['residual'])
         return [row['point_error'] for row in self.losses]
@@ -46,9 +50,12 @@ class Loss:
 
     def aggregated_loss(self) -> List[Tensor]:
         if not self._done:
-            self.weighted_point_error()
             for row in self.losses:
-                row['aggregated_loss'] = self._agg(row['weighted_error'])
+                if row.get('aggregated_loss') is None:      # rows reduced by the fused kernel arrive aggregated
+                    if row.get('point_error') is None:
+                        row['point_error'] = self.error_func(row['residual'])
+                    row['weighted_error'] = row['weighting'] * row['point_error']
+                    row['aggregated_loss'] = self._agg(row['weighted_error'])
             self._done = True
         return [row['aggregated_loss'] for row in self.losses]
 
@@ -87,8 +94,11 @@ class Loss:
 
 
 class Loss_handler:
-    def __init__(self, dataset=None) -> None:
+    def __init__(self, dataset=None, fused: bool = True) -> None:
         self.rows: List[dict] = []
+        self.fused = fused                 # use tde_residual_loss when the engine output allows it
+        self.fusion_report: Dict[str, str] = {}   # group -> 'fused' | reason it stayed on the torch path
+        self._programs: Dict[tuple, object] = {}
         self.update_dataset(dataset)
 
     def update_dataset(self, dataset):
@@ -108,9 +118,21 @@ class Loss_handler:
     def __call__(self, group_input: Dict, group_output: Dict, **kwargs) -> Loss:
         return self.calculate(group_input, group_output, **kwargs)
 
-    def calculate(self, batched_input, batched_output, power: int = 2, aggregation_method='mean') -> Loss:
+    def calculate(self, batched_input, batched_output, power: int = 2, aggregation_method='mean', fused=None) -> Loss:
+        use_fused = self.fused if fused is None else fused
+        fused_groups = {}
+        if (use_fused and power == 2 and aggregation_method == 'mean'
+                and getattr(batched_output, 'block', None) is not None and batched_output.block.is_cuda):
+            fused_groups = self._fused_rows(batched_input, batched_output)
         rows = []
         for spec in self.rows:
+            if not spec['custom'] and spec['group'] in fused_groups:
+                row = dict(spec)
+                row['residual'] = None
+                row['weighting'] = None
+                row['aggregated_loss'] = fused_groups[spec['group']].pop(0)
+                rows.append(row)
+                continue
             row = dict(spec)
             if spec['custom']:
                 row['residual'] = spec['evaluation'](batched_input, batched_output)
@@ -125,7 +147,64 @@ class Loss_handler:
             rows.append(row)
         return Loss(rows, aggregation_method, power)
 
+    # -- fused path ---------------------------------------------------------------------------
+    def _fused_rows(self, batched_input, out) -> Dict[str, list]:
+        """Launch the fused kernel for every group whose rows trace into a register program.
+        Returns {group: [row loss tensors in table order]}; other groups stay on the torch path."""
+        names = list(out.stream_row.keys())
+        n_stream_rows = out.block.shape[0]
+        launches, owners = [], []
+        for g, (lo, hi) in out.ranges.items():
+            specs = [r for r in self.rows if r['group'] == g and not r['custom']]
+            if not specs or g not in batched_input:
+                continue
+            group = batched_input[g]
+            key = (g, tuple(names), len(specs))
+            gp = self._programs.get(key)
+            try:
+                weights = [FL.eval_weight(sp, group, names) for sp in specs]
+                if gp is None:
+                    gp = FL.trace_group(group, specs, out.stream_row, n_stream_rows)
+                    for i, w in enumerate(weights):
+                        if isinstance(w, torch.Tensor):
+                            gp.weight_slot(i)
+                    self._programs[key] = gp
+                    self.fusion_report[g] = 'fused'
+                elif gp is False:
+                    continue
+            except FL.TraceError as exc:
+                self._programs[key] = False
+                self.fusion_report[g] = f'torch path: {exc}'
+                continue
+            n = hi - lo
+            aux = None
+            if gp.aux_names:
+                cols = []
+                for a in gp.aux_names:
+                    if a.startswith('__w'):
+                        w = weights[int(a[3:])]
+                        cols.append(w if isinstance(w, torch.Tensor) else torch.full((n,), float(w), device=out.block.device))
+                    else:
+                        cols.append(group.batchables[a].to(torch.float32))
+                aux = torch.stack(cols).contiguous()
+            for i, w in enumerate(weights):
+                if gp.weight_aux[i] is None:
+                    if isinstance(w, torch.Tensor):
+                        raise RuntimeError(f"weighting of group '{g}' changed from a constant to a per-point tensor")
+                    gp.prog.w_const[i] = float(w)
+            launches.append((gp, aux, lo, n))
+            owners.append((g, gp.prog.n_rows))
+        if not launches:
+            return {}
+        rows = FL.fused_rows(out.block, launches)
+        result, off = {}, 0
+        for g, k in owners:
+            result[g] = [rows[off + i] for i in range(k)]
+            off += k
+        return result
+
     def set_terms(self, loss_type, group, var_dict: Dict[str, Callable], weighting, custom: bool = False):
+        self._programs.clear()
         if self._group_names is not None and not custom:
             assert group in self._group_names, f"group '{group}' is not in the dataset"
         if not isinstance(weighting, dict):
