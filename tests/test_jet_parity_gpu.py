@@ -226,3 +226,20 @@ def test_empty_and_ragged_batches():
         assert o['u'].shape == (n,)
         assert torch.allclose(o['u'], net(x)[:, 0], rtol=1e-5, atol=1e-6)
         o['u_xx'].sum().backward()
+
+
+def test_recompute_mode_matches_stash_mode(monkeypatch):
+    """Batches whose stash would not fit switch to chunked recompute in backward; gradients must agree."""
+    from torch_de_b200 import engine as E
+    z, owl, params, groups = load('ldc_small')
+    wl = product_workload('ldc_small')
+    grads = {}
+    for frac in (0.55, 1e-9):
+        monkeypatch.setattr(E, 'STASH_FRACTION_OF_FREE', frac)
+        net, lins = load_net(wl, params, 'cuda')
+        pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+        x = torch.rand(5000, 2, generator=torch.Generator().manual_seed(1)).cuda() * 0.2 - 0.1
+        out = pinn(x)['all']
+        (out['u_xx'] * out['v_y'] + out['p_x'].pow(2)).mean().backward()
+        grads[frac] = torch.cat([p.grad.flatten().cpu() for lin in lins for p in (lin.weight, lin.bias)])
+    assert rel_l2(grads[1e-9], grads[0.55]) < 1e-5

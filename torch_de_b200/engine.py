@@ -55,6 +55,7 @@ class JetRunner:
         self._net.n_layers = len(self.lins)
         self._plans: Dict[int, _lib.TdePlan] = {}
         self._workspace: Optional[torch.Tensor] = None
+        self.chunking: Dict[tuple, int] = {}
 
     def _bind(self, tensors: Sequence[torch.Tensor]):
         n = len(self.lins)
@@ -113,18 +114,24 @@ class JetRunner:
         return x, out, stash
 
     def backward(self, x: torch.Tensor, tensors: Sequence[torch.Tensor], stash: torch.Tensor, seeds: torch.Tensor,
-                 flat_grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0) -> torch.Tensor:
+                 flat_grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0, seeds_ld: int = 0) -> torch.Tensor:
+        """seeds: [rows, B] block; with seeds_ld > 0 it is a column slice of a wider contiguous block whose row
+        pitch is seeds_ld (recompute mode passes views, no copy)."""
         B = x.shape[0]
         if flat_grad is None:
             flat_grad = torch.zeros(self.n_params, dtype=torch.float32, device=x.device)
         if B == 0:
             return flat_grad
-        seeds = seeds.contiguous()
+        if seeds_ld == 0:
+            seeds = seeds.contiguous()
+            seeds_ld = B
+        elif seeds.stride(1) != 1 or seeds.stride(0) != seeds_ld:
+            raise ValueError("seed slice does not have the declared row pitch")
         plan = self.plan(B)
         self._bind(tensors)
         ws = self._ws(plan.workspace_bytes, x.device)
         rc = _lib.lib().tde_jet_backward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, stash.data_ptr(),
-                                         seeds.data_ptr(), B, grad_scale, flat_grad.data_ptr(), ws.data_ptr(),
+                                         seeds.data_ptr(), seeds_ld, grad_scale, flat_grad.data_ptr(), ws.data_ptr(),
                                          self._stream(x.device))
         _lib.check(rc, "tde_jet_backward")
         return flat_grad
@@ -137,15 +144,37 @@ class JetRunner:
         return views
 
 
+# Largest activation stash kept from forward to backward, as a fraction of the free device memory at call
+# time.  Bigger batches switch to recompute mode: the forward keeps nothing and the backward re-runs the
+# forward chunk by chunk (+1/3 FLOPs, bounded memory) -- the cylinder config (2e6 pts/GPU x 10x512) needs it.
+STASH_FRACTION_OF_FREE = 0.35
+
+
 class _JetFunction(torch.autograd.Function):
     """out[J*n_out, B] = jets(net, x); differentiable w.r.t. the Linear parameters (not x: no caller needs it)."""
 
     @staticmethod
     def forward(ctx, x, runner: JetRunner, *params):
         need = any(ctx.needs_input_grad[2:])
-        xc, out, stash = runner.forward(x, params, need_stash=need)
+        ctx.chunk = 0
+        if need and x.shape[0] > 0 and x.is_cuda:
+            key = (x.shape[0], STASH_FRACTION_OF_FREE)
+            if key not in runner.chunking:      # decided once per batch size so every step allocates the same blocks
+                free, _ = torch.cuda.mem_get_info(x.device)
+                free += torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
+                budget = STASH_FRACTION_OF_FREE * free
+                total = runner.plan(x.shape[0]).stash_bytes
+                chunk = 0
+                if total > budget:
+                    n_chunks = int(-(-total // budget))
+                    tile = runner.plan(x.shape[0]).tile_points
+                    chunk = max(tile, -(-(-(-x.shape[0] // n_chunks)) // tile) * tile)
+                runner.chunking[key] = chunk
+            ctx.chunk = runner.chunking[key]
+        xc, out, stash = runner.forward(x, params, need_stash=need and ctx.chunk == 0)
         ctx.runner = runner
         ctx.stash = stash
+        ctx.need = need
         ctx.save_for_backward(xc, *params)
         return out
 
@@ -153,9 +182,19 @@ class _JetFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         x, *params = ctx.saved_tensors
         runner: JetRunner = ctx.runner
-        if ctx.stash is None and x.shape[0] > 0:
+        B = x.shape[0]
+        if not ctx.need and B > 0:
             raise RuntimeError("backward through a jet forward that kept no stash")
-        flat = runner.backward(x, params, ctx.stash, grad_out)
+        if ctx.chunk == 0:
+            flat = runner.backward(x, params, ctx.stash, grad_out)
+        else:   # recompute mode
+            flat = torch.zeros(runner.n_params, dtype=torch.float32, device=x.device)
+            grad_out = grad_out.contiguous()
+            for lo in range(0, B, ctx.chunk):
+                hi = min(B, lo + ctx.chunk)
+                xc, _, stash = runner.forward(x[lo:hi], params, need_stash=True)
+                runner.backward(xc, params, stash, grad_out[:, lo:hi], flat_grad=flat, seeds_ld=B)
+                del stash
         return (None, None, *runner.split_flat(flat))
 
 
