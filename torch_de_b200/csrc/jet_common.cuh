@@ -307,6 +307,18 @@ __device__ __forceinline__ void act_backward(int act, const float (&st)[S::J], c
 //   acc[pc][j] += sum_k A[k][col0+pc] * Bq[k][q(g,j)]      (A: smem tile, K-major; Bq: streamed chunks)
 // Consumers wait on full[stage], compute kKC reduction rows, release with one arrive per warp.
 // ---------------------------------------------------------------------------------------------
+// 3xTF32 split: hi = round-to-nearest TF32 of x, lo = round-to-nearest TF32 of (x - hi).  Rounding (not the
+// hardware's truncation) keeps the split unbiased, so the dropped lo*lo / sub-TF32 bits do not accumulate over K.
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - hi);
+}
+
 // packed FP32 pairs (Blackwell fma.rn.f32x2: two FMAs per issue slot and per register-file read)
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
     uint64_t r;

@@ -1,6 +1,7 @@
 // One translation unit per compiled jet spec: built with -DTDE_NF=<n> -DTDE_SMASK=<mask>.
 #include "jet_forward.cuh"
 #include "jet_backward.cuh"
+#include "jet_forward_tc.cuh"
 #include "jet_launch.h"
 
 #define TDE_CAT_(a, b, c, d) a##b##_##d
@@ -21,6 +22,14 @@ cudaError_t TDE_CAT(launch_backward_, TDE_NF, _, TDE_SMASK)(const JetParams& p, 
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k<<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p, int grid, int smem, cudaStream_t st) {
+    auto k = jet_forward_tc_kernel<TDE_NF, TDE_SMASK>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kTcThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 

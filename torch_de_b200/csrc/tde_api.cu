@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,8 +65,9 @@ struct ScopedTimer {
 struct Dispatch {
     int nf, smask;
     tde::JetLauncher fwd, bwd;
+    tde::TcLauncher fwd_tc;
 };
-#define TDE_ROW(nf, sm) {nf, sm, tde::launch_forward_##nf##_##sm, tde::launch_backward_##nf##_##sm},
+#define TDE_ROW(nf, sm) {nf, sm, tde::launch_forward_##nf##_##sm, tde::launch_backward_##nf##_##sm, tde::launch_forward_tc_##nf##_##sm},
 const Dispatch kDispatch[] = {TDE_SPEC_LIST(TDE_ROW)};
 #undef TDE_ROW
 
@@ -86,7 +88,10 @@ struct Geometry {
     int n_ctas;
     int64_t n_tiles;
     // packed weight offsets
-    int64_t o_w_in, o_b_in, o_wt, o_wn, o_bh, o_wo, o_bo, packed_floats;
+    int64_t o_w_in, o_b_in, o_wt, o_wn, o_bh, o_wo, o_bo, o_wc, packed_floats;
+    // tcgen05 forward (wide layers)
+    int use_tc, tc_mb, tc_stages, tc_smem, tc_nacc;
+    int64_t tc_tiles;
     // per-CTA partial gradient slab
     int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo, gp_stride;
     int64_t o_gpart;
@@ -213,6 +218,28 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.o_bh = o;   o += (int64_t)(L - 1) * g.W;
     g.o_wo = o;   o = align_up(o + (int64_t)g.n_out * g.W, 4);
     g.o_bo = o;   o = align_up(o + g.n_out, 4);
+    // tcgen05 forward: W in {128, 256}, accumulators of all neuron blocks fit 256 TMEM columns, backward tile is a
+    // multiple of the 16-point tensor tile.  TDE_NO_TC=1 forces the FFMA path (A/B measurements, debugging).
+    g.use_tc = 0;
+    {
+        const int Ntc = tde::kTcPoints * g.J;
+        const int mb = g.W / 128;
+        const char* no_tc = getenv("TDE_NO_TC");
+        if ((g.W == 128 || g.W == 256) && L >= 2 && mb * Ntc <= 512 && g.TP % tde::kTcPoints == 0 && !(no_tc && no_tc[0] == '1')) {
+            const int64_t lbz = (Ntc / 8) * 128 + 16;
+            const int64_t fixed = 256 + 2 * (g.W / 4) * lbz + 4 * ((int64_t)g.n_out * g.W + tde::kTcPoints * g.d_in + (int64_t)g.J * g.n_out * tde::kTcPoints);
+            const int64_t chunk = (int64_t)mb * 2 * 2 * 2048;
+            for (int st = tde::kMaxStages; st >= 2; --st)
+                if (fixed + st * chunk <= kSmemLimit) {
+                    g.use_tc = 1; g.tc_mb = mb; g.tc_stages = st; g.tc_smem = (int)(fixed + st * chunk);
+                    g.tc_nacc = std::min(3, 512 / (mb * Ntc));
+                    break;
+                }
+        }
+        g.tc_tiles = B > 0 ? (B + tde::kTcPoints - 1) / tde::kTcPoints : 0;
+    }
+    o = align_up(o, 64);
+    g.o_wc = o;   if (g.use_tc) o += (int64_t)(L - 1) * 2 * WW;
     g.packed_floats = align_up(o, 64);
 
     int64_t q = 0;
@@ -291,18 +318,49 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* _
     }
 }
 
+// tcgen05 operand image of the hidden weights: per layer, per 8-k chunk: [hi|lo][neuron block][k group of 4][16 row
+// groups][8 rows][4 k] -- exactly the shared-memory layout of the K-major SWIZZLE_NONE UMMA A operand, split 3xTF32.
+__global__ void pack_tc_weights_kernel(const __grid_constant__ PackArgs a, float* __restrict__ wc, int MB) {
+    const int W = a.W;
+    const int64_t per_layer = 2LL * W * W;
+    const int64_t total = (int64_t)(a.L - 1) * per_layer;
+    const int chunk = MB * 2 * 2 * 512;   // floats per chunk
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)(i / per_layer) + 1;
+        int64_t r = i % per_layer;
+        const int ks = (int)(r / chunk);
+        int c = (int)(r % chunk);
+        const int hl = c / (MB * 1024); c %= MB * 1024;
+        const int mb = c / 1024;        c %= 1024;
+        const int kg = c / 512;         c %= 512;
+        const int rg = c / 32;          c %= 32;
+        const int rr = c / 4, kk = c % 4;
+        const int n = mb * 128 + rg * 8 + rr, k = ks * 8 + kg * 4 + kk;
+        float v = 0.0f;
+        if (n < a.width && k < a.width) v = a.net.layers[l].weight[(int64_t)n * a.width + k];
+        float hi, lo;
+        tde::split_tf32(v, hi, lo);
+        wc[i] = hl ? lo : hi;
+    }
+}
+
 int launch_pack(const TdeNet* net, const Geometry& g, float* ws, bool want_wt, bool want_wn, cudaStream_t st) {
     PackArgs a{};
     a.net = *net;
     a.W = g.W; a.L = g.L; a.d_in = g.d_in; a.n_out = g.n_out; a.width = g.width;
     a.o_w_in = g.o_w_in; a.o_b_in = g.o_b_in; a.o_wt = g.o_wt; a.o_wn = g.o_wn; a.o_bh = g.o_bh;
-    a.o_wo = g.o_wo; a.o_bo = g.o_bo; a.total = g.packed_floats;
+    a.o_wo = g.o_wo; a.o_bo = g.o_bo; a.total = g.o_bo + g.n_out;
     a.want_wt = want_wt; a.want_wn = want_wn;
     const int threads = 256;
     const int blocks = (int)std::min<int64_t>((g.packed_floats + threads - 1) / threads, 148 * 8);
     pack_weights_kernel<<<blocks, threads, 0, st>>>(a, ws);
     ++g_launches;
     TDE_CUDA(cudaGetLastError());
+    if (want_wt && g.use_tc) {
+        pack_tc_weights_kernel<<<148 * 4, threads, 0, st>>>(a, ws + g.o_wc, g.tc_mb);
+        ++g_launches;
+        TDE_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -575,10 +633,23 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = (float*)workspace;
     if (int rc = launch_pack(net, g, ws, true, false, st)) return rc;
-    tde::JetParams p;
-    fill_params(g, spec, ws, &p);
-    p.x = x; p.B = n_points; p.out = out; p.ld_out = ld_out; p.stash = stash; p.n_stages = g.stages_fwd;
-    {
+    if (g.use_tc) {
+        tde::TcParams t{};
+        t.x = x; t.B = n_points; t.n_tiles = g.tc_tiles;
+        t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb; t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc;
+        for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
+        t.w_in = ws + g.o_w_in; t.b_in = ws + g.o_b_in; t.wc = ws + g.o_wc; t.b_hidden = ws + g.o_bh;
+        t.w_out = ws + g.o_wo; t.b_out = ws + g.o_bo;
+        t.out = out; t.ld_out = ld_out; t.stash = stash;
+        t.stash_layer_stride = g.n_tiles * g.W * (int64_t)g.TP * g.J;
+        t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), g.tc_tiles));
+        ScopedTimer timer(st, 0);
+        TDE_CUDA(g.disp->fwd_tc(t, grid, g.tc_smem, st));
+    } else {
+        tde::JetParams p;
+        fill_params(g, spec, ws, &p);
+        p.x = x; p.B = n_points; p.out = out; p.ld_out = ld_out; p.stash = stash; p.n_stages = g.stages_fwd;
         ScopedTimer timer(st, 0);
         TDE_CUDA(g.disp->fwd(p, g.n_ctas, g.smem_fwd, st));
     }
