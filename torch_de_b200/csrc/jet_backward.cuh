@@ -42,6 +42,14 @@ __device__ __forceinline__ void load_row_vec(const float* src, float (&v)[S::PT]
 #pragma unroll
         for (int c = 0; c < S::J; ++c) v[pt][c] = flat[pt * S::J + c];
 }
+// stash layout [layer][tile][jet column][neuron]
+template <class S>
+__device__ __forceinline__ void load_stash_cols(const float* src, int W, float (&v)[S::PT][S::J]) {
+#pragma unroll
+    for (int pt = 0; pt < S::PT; ++pt)
+#pragma unroll
+        for (int c = 0; c < S::J; ++c) v[pt][c] = __ldcs(src + (size_t)(pt * S::J + c) * W);
+}
 template <class S>
 __device__ __forceinline__ void store_row_vec_b(float* dst, const float (&v)[S::PT][S::J]) {
     float flat[S::PJ];
@@ -171,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
             for (int j = 0; j < kNT; ++j) {
                 const int n = g + NG * j;
                 float st[PT][J], hb[PT][J];
-                load_row_vec<S>(stash_l + (size_t)n * TPJ + col0, st);
+                load_stash_cols<S>(stash_l + (size_t)col0 * W + n, W, st);
                 float wo[TDE_MAX_OUT];
 #pragma unroll
                 for (int o = 0; o < TDE_MAX_OUT; ++o) wo[o] = o < p.n_out ? wout_s[o * W + n] : 0.0f;
@@ -239,9 +247,9 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
             for (int kb = 0; kb < W / kblk; ++kb) {
                 // stage Z_{l-1} rows [kb*kblk, +kblk): recomputed from the stash
                 for (int item = tid; item < kblk * PG; item += kComputeThreads) {
-                    const int r = item / PG, grp = item - r * PG;
+                    const int grp = item / kblk, r = item - grp * kblk;   // consecutive threads -> consecutive neurons
                     float st[PT][J], z[PT][J];
-                    load_row_vec<S>(stash_prev + (size_t)(kb * kblk + r) * TPJ + grp * PJ, st);
+                    load_stash_cols<S>(stash_prev + (size_t)(grp * PJ) * W + kb * kblk + r, W, st);
 #pragma unroll
                     for (int pt = 0; pt < PT; ++pt) act_recompute<S>(p.act, st[pt], z[pt]);
                     store_row_vec_b<S>(ubuf + (size_t)r * pitch + grp * PJ, z);
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
             for (int j = 0; j < kNT; ++j) {
                 const int n = g + NG * j;
                 float st[PT][J], hb[PT][J];
-                load_row_vec<S>(stash_l1 + (size_t)n * TPJ + col0, st);
+                load_stash_cols<S>(stash_l1 + (size_t)col0 * W + n, W, st);
 #pragma unroll
                 for (int pt = 0; pt < PT; ++pt) {
                     float zb[J], zdummy[J];

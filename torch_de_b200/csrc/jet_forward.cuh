@@ -24,16 +24,13 @@ __device__ __forceinline__ void store_row_vec(float* dst, const float (&v)[S::PT
     for (int i = 0; i < S::NV; ++i)
         *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(flat[4 * i], flat[4 * i + 1], flat[4 * i + 2], flat[4 * i + 3]);
 }
+// stash layout [layer][tile][jet column][neuron]: a warp's 32 consecutive neurons store one 128 B line per column
 template <class S>
-__device__ __forceinline__ void store_row_vec_stream(float* dst, const float (&v)[S::PT][S::J]) {
-    float flat[S::PJ];
+__device__ __forceinline__ void store_stash_cols(float* dst, int W, const float (&v)[S::PT][S::J]) {
 #pragma unroll
     for (int pt = 0; pt < S::PT; ++pt)
 #pragma unroll
-        for (int c = 0; c < S::J; ++c) flat[pt * S::J + c] = v[pt][c];
-#pragma unroll
-    for (int i = 0; i < S::NV; ++i)
-        __stcs(reinterpret_cast<float4*>(dst + 4 * i), make_float4(flat[4 * i], flat[4 * i + 1], flat[4 * i + 2], flat[4 * i + 3]));
+        for (int c = 0; c < S::J; ++c) __stcs(dst + (size_t)(pt * S::J + c) * W, v[pt][c]);
 }
 
 template <int NF, int SMASK>
@@ -145,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_forward_kernel(const __grid_c
                 }
                 if (active) {
                     store_row_vec<S>(A + (size_t)n * pitch + col0, zt);
-                    if (stash_tile) store_row_vec_stream<S>(stash_tile + (size_t)n * (TP * J) + col0, st);
+                    if (stash_tile) store_stash_cols<S>(stash_tile + (size_t)col0 * W + n, W, st);
                 }
             }
         }
@@ -190,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_forward_kernel(const __grid_c
                 }
                 if (active) {
                     store_row_vec<S>(A + (size_t)n * pitch + col0, zt);
-                    if (stash_l) store_row_vec_stream<S>(stash_l + (size_t)n * (TP * J) + col0, st);
+                    if (stash_l) store_stash_cols<S>(stash_l + (size_t)col0 * W + n, W, st);
                 }
             }
             compute_sync();

@@ -25,6 +25,7 @@ struct TcParams {
     int64_t n_tiles;       // 16-point tiles
     int d_in, n_out, L, W, act, MB;   // MB = W / 128
     int n_stages;
+    int dbg;               // bit0: skip weight streaming (timing experiment only)
     int n_acc;             // TMEM accumulator sets: 3 = {small terms, main even k-steps, main odd k-steps}, 2, or 1
     int first_in[TDE_MAX_FIRST];
     const float* w_in;     // [W][d_in]
@@ -35,7 +36,7 @@ struct TcParams {
     const float* b_out;
     float* out;
     int64_t ld_out;
-    float* stash;          // FFMA-backward layout [L][n_tiles_bw][W][TPbw*J]
+    float* stash;          // [L][n_tiles_bw][TPbw*J columns][W]
     int64_t stash_layer_stride;
     int tiles_per_bw_tile; // TPbw / 16
 };
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                 for (int l = 1; l < p.L; ++l) {
                     const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wc) + (size_t)(l - 1) * n_ks * chunk_bytes;
                     for (int ks = 0; ks < n_ks; ++ks) {
+                        if (p.dbg & 1) continue;
                         mbar_wait(&empty[s], ph ^ 1);   // spin: a chunk is consumed in ~150 ns, the refill must be prompt
                         mbar_expect_tx(&full[s], chunk_bytes);
                         bulk_g2s(wst + (size_t)s * chunk_bytes, src + (size_t)ks * chunk_bytes, chunk_bytes, &full[s]);
@@ -150,12 +152,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                     act_ph ^= 1;
                     tc_fence_after();
                     for (int ks = 0; ks < n_ks; ++ks) {
-                        mbar_wait(&full[s], ph);
+                        if (!(p.dbg & 1)) mbar_wait(&full[s], ph);
                         tc_fence_after();
                         const uint32_t wbase = smem_u32(wst + (size_t)s * chunk_bytes);
                         const uint64_t b_hi = umma_desc(smem_u32(zhi) + ks * 2 * LBZ, LBZ, 128);
                         const uint64_t b_lo = umma_desc(smem_u32(zlo) + ks * 2 * LBZ, LBZ, 128);
-                        for (int mb = 0; mb < MB; ++mb) {
+                        for (int mb = 0; mb < MB && !(p.dbg & 2); ++mb) {
                             const uint64_t a_hi = umma_desc(wbase + (uint32_t)(0 * MB + mb) * 4096u, 2048, 128);
                             const uint64_t a_lo = umma_desc(wbase + (uint32_t)(1 * MB + mb) * 4096u, 2048, 128);
                             // The tensor core rounds its FP32 accumulator toward zero after every MMA: that bias, not the
@@ -209,7 +211,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                 if (p.stash) {
                     const int64_t bw_tile = tile / p.tiles_per_bw_tile;
                     const int sub = (int)(tile - bw_tile * p.tiles_per_bw_tile);
-                    stash_row = p.stash + ((size_t)bw_tile * W + n) * ((size_t)p.tiles_per_bw_tile * N) + (size_t)sub * N;
+                    // [layer][backward tile][jet column][neuron]: this thread's neuron, first column of its 16-point sub-tile
+                    stash_row = p.stash + ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N) * W + n;
                 }
 
                 for (int l = 0; l < p.L; ++l) {
@@ -277,9 +280,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                     }
                     if (srow) {
 #pragma unroll
-                        for (int i = 0; i < N / 4; ++i)
-                            __stcs(reinterpret_cast<float4*>(srow + 4 * i),
-                                   make_float4(hbuf[4 * i], hbuf[4 * i + 1], hbuf[4 * i + 2], hbuf[4 * i + 3]));
+                        for (int i = 0; i < N; ++i) __stcs(srow + (size_t)i * W, hbuf[i]);   // one 128 B line per warp store
                     }
                     if (l < p.L - 1) {
                         // publish: smem writes -> async proxy, TMEM reads retired, then one arrive per warp

@@ -637,6 +637,7 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
         tde::TcParams t{};
         t.x = x; t.B = n_points; t.n_tiles = g.tc_tiles;
         t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb; t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc;
+        { const char* d = getenv("TDE_TC_DBG"); t.dbg = d ? atoi(d) : 0; }
         for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
         t.w_in = ws + g.o_w_in; t.b_in = ws + g.o_b_in; t.wc = ws + g.o_wc; t.b_hidden = ws + g.o_bh;
         t.w_out = ws + g.o_wo; t.b_out = ws + g.o_bo;
