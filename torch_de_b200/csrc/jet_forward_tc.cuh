@@ -18,6 +18,7 @@ namespace tde {
 constexpr int kTcPoints = 16;      // points per tile
 constexpr int kTcKC = 8;           // k rows per weight chunk (= one tf32 MMA K step)
 constexpr int kTcThreads = 384;    // 4 control warps + 8 epilogue warps
+constexpr int kTcCluster = 2;      // CTAs per cluster: each loads 1/2 of every weight chunk and multicasts it to both
 
 struct TcParams {
     const float* x;
@@ -25,6 +26,7 @@ struct TcParams {
     int64_t n_tiles;       // 16-point tiles
     int d_in, n_out, L, W, act, MB;   // MB = W / 128
     int n_stages;
+    long long* dbg_buf;    // optional cycle stamps (TDE_TC_DBG bit 2)
     int dbg;               // bit0: skip weight streaming (timing experiment only)
     int n_acc;             // TMEM accumulator sets: 3 = {small terms, main even k-steps, main odd k-steps}, 2, or 1
     int first_in[TDE_MAX_FIRST];
@@ -41,6 +43,11 @@ struct TcParams {
     int tiles_per_bw_tile; // TPbw / 16
 };
 
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
+    // K-major SWIZZLE_128B: rows of 128 B, 8-row groups sbo_bytes apart; layout_type = 2, version = 1
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // K-major, SWIZZLE_NONE canonical layout; version = 1 (sm_100)
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
@@ -58,6 +65,33 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -77,8 +111,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     using S = JetSpecT<NF, SMASK>;
     constexpr int J = S::J;
     constexpr int N = kTcPoints * J;             // jet columns per tile (multiple of 16)
-    constexpr uint32_t LBZ = (N / 8) * 128 + 16;  // byte stride between 4-k groups of the activation planes (+16: bank skew)
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // activation planes: K-major SWIZZLE_128B atoms of 8 jet columns x 32 k (1024 B), ordered [k/32][col/8].  A warp's 32
+    // consecutive neurons write one full 128 B row per column (conflict-free) and every MMA operand row is 128 B aligned.
+    constexpr uint32_t ATOMK = (N / 8) * 1024;   // bytes between k-atoms
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
 
     const int W = p.W, MB = p.MB;
     const int n_stages = p.n_stages;
@@ -87,8 +123,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     uint64_t* act_ready = empty + kMaxStages;
     uint64_t* acc_ready = act_ready + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
-    unsigned char* zhi = smem_raw + 256;
-    const uint32_t z_plane = (uint32_t)(W / 4) * LBZ;
+    unsigned char* zhi = smem_raw + 1024;
+    const uint32_t z_plane = (uint32_t)(W / 32) * ATOMK;
     unsigned char* zlo = zhi + z_plane;
     const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;   // [hi|lo][mb][kgroup 2][16 row groups][8][4] floats*4
     unsigned char* wst = zlo + z_plane;                              // [n_stages][chunk_bytes]
@@ -104,7 +140,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], kTcCluster);   // one tcgen05.commit arrival from the MMA issuer of every CTA in the cluster
         }
         mbar_init(act_ready, n_epi_warps);
         mbar_init(acc_ready, 1);
@@ -116,8 +152,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();   // peers' barriers are initialised before any multicast copy / remote arrive can land
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = cluster_ctarank();
+    // tile schedule: cluster c handles tile pairs c, c + n_clusters, ...; rank r takes tile 2*pair + r.  Both CTAs run the
+    // same number of iterations (a rank without a real tile computes a dummy one) so the shared weight pipeline stays in step.
+    const int64_t n_pairs = (p.n_tiles + kTcCluster - 1) / kTcCluster;
+    const int64_t first_pair = blockIdx.x / kTcCluster, pair_step = gridDim.x / kTcCluster;
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
@@ -125,14 +167,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
             // ===== producer: weight chunks (already hi/lo split, UMMA core-matrix order) =====
             int s = 0;
             uint32_t ph = 0;
-            for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const uint32_t part = chunk_bytes / kTcCluster;
+            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
                 for (int l = 1; l < p.L; ++l) {
                     const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wc) + (size_t)(l - 1) * n_ks * chunk_bytes;
                     for (int ks = 0; ks < n_ks; ++ks) {
                         if (p.dbg & 1) continue;
-                        mbar_wait(&empty[s], ph ^ 1);   // spin: a chunk is consumed in ~150 ns, the refill must be prompt
-                        mbar_expect_tx(&full[s], chunk_bytes);
-                        bulk_g2s(wst + (size_t)s * chunk_bytes, src + (size_t)ks * chunk_bytes, chunk_bytes, &full[s]);
+                        mbar_wait(&empty[s], ph ^ 1);   // both CTAs have finished reading this stage
+                        mbar_expect_tx(&full[s], chunk_bytes);      // my part + the peer's part will land here
+                        bulk_g2s_mc(wst + (size_t)s * chunk_bytes + crank * part, src + (size_t)ks * chunk_bytes + crank * part, part,
+                                    &full[s], (uint16_t)((1u << kTcCluster) - 1));
                         if (++s == n_stages) {
                             s = 0;
                             ph ^= 1;
@@ -140,48 +184,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                     }
                 }
             }
-        } else if (tid == 32) {
-            // ===== MMA issuer =====
+        } else if (warp == 1) {
+            // ===== MMA issuer: the whole warp runs the control flow converged, one elected lane issues =====
+            // (a UTCHMMA inside divergent code is wrapped by the compiler in an ELECT/branch loop: ~100 cycles each)
+            const bool leader = elect_one();
             // instruction descriptor: D=F32, A=B=TF32, both K-major, N, M=128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t b_hi0 = umma_desc_sw128(smem_u32(zhi), 1024);
+            const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
+            const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
+            const uint32_t stage_step = chunk_bytes >> 4, blk_step = 4096u >> 4;
+            const int n_acc = p.n_acc;
             int s = 0;
             uint32_t ph = 0, act_ph = 0;
-            for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
+                const int64_t tile = pair * kTcCluster + crank;
                 for (int l = 1; l < p.L; ++l) {
+                    const bool mstamp = p.dbg_buf && blockIdx.x == 0 && tile == 0 && l == 2 && lane == 0;
+                    if (mstamp) p.dbg_buf[8] = clock64();
                     mbar_wait(act_ready, act_ph);   // Z planes of layer l-1 are in smem, TMEM accumulators are free
                     act_ph ^= 1;
                     tc_fence_after();
+                    if (mstamp) p.dbg_buf[9] = clock64();
                     for (int ks = 0; ks < n_ks; ++ks) {
                         if (!(p.dbg & 1)) mbar_wait(&full[s], ph);
                         tc_fence_after();
-                        const uint32_t wbase = smem_u32(wst + (size_t)s * chunk_bytes);
-                        const uint64_t b_hi = umma_desc(smem_u32(zhi) + ks * 2 * LBZ, LBZ, 128);
-                        const uint64_t b_lo = umma_desc(smem_u32(zlo) + ks * 2 * LBZ, LBZ, 128);
-                        for (int mb = 0; mb < MB && !(p.dbg & 2); ++mb) {
-                            const uint64_t a_hi = umma_desc(wbase + (uint32_t)(0 * MB + mb) * 4096u, 2048, 128);
-                            const uint64_t a_lo = umma_desc(wbase + (uint32_t)(1 * MB + mb) * 4096u, 2048, 128);
+                        if (leader && !(p.dbg & 2)) {
+                            // k-step ks: atom ks/4, then 32 B (8 tf32) per step inside the 128 B swizzled row
+                            const uint32_t koff = ((uint32_t)(ks >> 2) * ATOMK + (uint32_t)(ks & 3) * 32u) >> 4;
+                            const uint64_t b_hi = b_hi0 + (uint64_t)koff;
+                            const uint64_t b_lo = b_lo0 + (uint64_t)koff;
+                            const uint64_t a_stage = a0 + (uint64_t)(s * stage_step);
                             // The tensor core rounds its FP32 accumulator toward zero after every MMA: that bias, not the
-                            // TF32 split, limits accuracy.  Keep the 2^-11-sized cross terms in their own accumulator
-                            // and alternate the main term over two accumulators; the epilogue adds them in FP32 (RN).
-                            const uint32_t d_small = tmem_base + (uint32_t)(mb * N);
-                            uint32_t d_main = d_small, first_main = ks == 0, first_small = ks == 0;
-                            if (p.n_acc == 3) {
-                                d_main = tmem_base + (uint32_t)((MB * (1 + (ks & 1)) + mb) * N);
-                                first_main = ks < 2;
-                            } else if (p.n_acc == 2) {
-                                d_main = tmem_base + (uint32_t)((MB + mb) * N);
+                            // TF32 split, limits accuracy.  Keep the 2^-11-sized cross terms in their own accumulator and
+                            // alternate the main term over two accumulators; the epilogue adds them in FP32 (RN).
+                            const uint32_t main_set = n_acc == 3 ? (uint32_t)(1 + (ks & 1)) : (n_acc == 2 ? 1u : 0u);
+                            const uint32_t acc_main = n_acc == 3 ? (uint32_t)(ks >= 2) : (n_acc == 2 ? (uint32_t)(ks > 0) : 1u);
+                            for (int mb = 0; mb < MB; ++mb) {
+                                const uint64_t a_hi = a_stage + (uint64_t)(mb * blk_step);
+                                const uint64_t a_lo = a_stage + (uint64_t)((MB + mb) * blk_step);
+                                const uint32_t d_small = tmem_base + (uint32_t)(mb * N);
+                                const uint32_t d_main = tmem_base + (uint32_t)((main_set * MB + mb) * N);
+                                umma_tf32(d_small, a_lo, b_hi, idesc, ks > 0);
+                                umma_tf32(d_small, a_hi, b_lo, idesc, 1);
+                                umma_tf32(d_main, a_hi, b_hi, idesc, acc_main);
                             }
-                            umma_tf32(d_small, a_lo, b_hi, idesc, !first_small);
-                            umma_tf32(d_small, a_hi, b_lo, idesc, 1);
-                            umma_tf32(d_main, a_hi, b_hi, idesc, p.n_acc == 1 ? 1u : !first_main);
+                            umma_commit_mc(&empty[s], (uint16_t)((1u << kTcCluster) - 1));   // stage is free in BOTH CTAs' view
                         }
-                        umma_commit(&empty[s]);      // frees the weight stage when these MMAs have read it
+                        __syncwarp();
                         if (++s == n_stages) {
                             s = 0;
                             ph ^= 1;
                         }
                     }
-                    umma_commit(acc_ready);          // accumulators of layer l complete
+                    if (leader) umma_commit(acc_ready);  // accumulators of layer l complete
+                    __syncwarp();
+                    if (mstamp) p.dbg_buf[10] = clock64();
                 }
             }
         }
@@ -197,10 +255,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
 
             for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
             // byte offset of element (col, k = n) inside a Z plane
-            const uint32_t zrow = (uint32_t)(n >> 2) * LBZ + (uint32_t)(n & 3) * 4u;
+            const uint32_t zrow = (uint32_t)(n >> 5) * ATOMK + (uint32_t)(n & 3) * 4u;   // k-atom + byte within the 16 B chunk
+            const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;                                // 16 B chunk index before the swizzle
             uint32_t acc_ph = 0;
 
-            for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
+                const int64_t tile = pair * kTcCluster + crank;     // may be a dummy tile (>= n_tiles): nothing is written
                 const int64_t pbase = tile * kTcPoints;
                 for (int i = et; i < kTcPoints * p.d_in; i += n_epi) {
                     const int64_t gp = pbase + i / p.d_in;
@@ -208,7 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                 }
                 epi_sync();
                 float* stash_row = nullptr;
-                if (p.stash) {
+                if (p.stash && tile < p.n_tiles) {
                     const int64_t bw_tile = tile / p.tiles_per_bw_tile;
                     const int sub = (int)(tile - bw_tile * p.tiles_per_bw_tile);
                     // [layer][backward tile][jet column][neuron]: this thread's neuron, first column of its 16-point sub-tile
@@ -238,9 +298,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                             for (int q = 0; q < S::NS; ++q) hbuf[pt * J + 1 + NF + q] = 0.0f;
                         }
                     } else {
+                        const bool stamp = p.dbg_buf && blockIdx.x == 0 && n == 0 && tile == 0 && l == 2;
+                        if (stamp) p.dbg_buf[0] = clock64();
                         mbar_wait(acc_ready, acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
+                        if (stamp) p.dbg_buf[1] = clock64();
                         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
 #pragma unroll
                         for (int c0 = 0; c0 < N; c0 += 16) tmem_ld16(taddr + c0, hbuf + c0);
@@ -258,6 +321,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                         const float bn = __ldg(p.b_hidden + (size_t)(l - 1) * W + n);
 #pragma unroll
                         for (int pt = 0; pt < kTcPoints; ++pt) hbuf[pt * J] += bn;
+                        if (stamp) p.dbg_buf[2] = clock64();
                     }
                     // jet activation, stash, split and store the next B operand
                     float* srow = stash_row ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
@@ -271,23 +335,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                         for (int c = 0; c < J; ++c) {
                             hbuf[pt * J + c] = h[c];     // (t | h_c) for the stash
                             const int col = pt * J + c;
-                            const uint32_t off = zrow + (uint32_t)(col >> 3) * 128u + (uint32_t)(col & 7) * 16u;
+                            const uint32_t off = zrow + (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u + ((kchunk ^ (uint32_t)(col & 7)) << 4);
                             float hi, lo;
                             split_tf32(z[c], hi, lo);
                             *reinterpret_cast<float*>(zhi + off) = hi;
                             *reinterpret_cast<float*>(zlo + off) = lo;
                         }
                     }
+                    const bool stamp2 = p.dbg_buf && blockIdx.x == 0 && n == 0 && tile == 0 && l == 2;
+                    if (stamp2) p.dbg_buf[3] = clock64();
                     if (srow) {
 #pragma unroll
                         for (int i = 0; i < N; ++i) __stcs(srow + (size_t)i * W, hbuf[i]);   // one 128 B line per warp store
                     }
+                    if (stamp2) p.dbg_buf[4] = clock64();
                     if (l < p.L - 1) {
                         // publish: smem writes -> async proxy, TMEM reads retired, then one arrive per warp
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(act_ready);
+                        if (stamp2) p.dbg_buf[5] = clock64();
                     }
                 }
                 epi_sync();   // every neuron's last-layer z is in the planes
@@ -297,10 +365,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                     float y[TDE_MAX_OUT];
 #pragma unroll
                     for (int o = 0; o < TDE_MAX_OUT; ++o) y[o] = 0.0f;
-                    const uint32_t cbase = (uint32_t)(col >> 3) * 128u + (uint32_t)(col & 7) * 16u;
+                    const uint32_t cbase = (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u;
                     for (int kg = 0; kg < W / 4; ++kg) {
-                        const float4 a = *reinterpret_cast<const float4*>(zhi + (uint32_t)kg * LBZ + cbase);
-                        const float4 b = *reinterpret_cast<const float4*>(zlo + (uint32_t)kg * LBZ + cbase);
+                        const uint32_t o4 = (uint32_t)(kg >> 3) * ATOMK + cbase + ((((uint32_t)kg & 7u) ^ (uint32_t)(col & 7)) << 4);
+                        const float4 a = *reinterpret_cast<const float4*>(zhi + o4);
+                        const float4 b = *reinterpret_cast<const float4*>(zlo + o4);
                         const float zz[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
 #pragma unroll
                         for (int o = 0; o < TDE_MAX_OUT; ++o)
@@ -327,6 +396,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();   // no CTA may exit while a peer can still multicast into it or arrive on its barriers
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 

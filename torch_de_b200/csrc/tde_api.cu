@@ -226,8 +226,8 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         const int mb = g.W / 128;
         const char* no_tc = getenv("TDE_NO_TC");
         if ((g.W == 128 || g.W == 256) && L >= 2 && mb * Ntc <= 512 && g.TP % tde::kTcPoints == 0 && !(no_tc && no_tc[0] == '1')) {
-            const int64_t lbz = (Ntc / 8) * 128 + 16;
-            const int64_t fixed = 256 + 2 * (g.W / 4) * lbz + 4 * ((int64_t)g.n_out * g.W + tde::kTcPoints * g.d_in + (int64_t)g.J * g.n_out * tde::kTcPoints);
+            const int64_t atomk = (Ntc / 8) * 1024;
+            const int64_t fixed = 1024 + 2 * (g.W / 32) * atomk + 4 * ((int64_t)g.n_out * g.W + tde::kTcPoints * g.d_in + (int64_t)g.J * g.n_out * tde::kTcPoints);
             const int64_t chunk = (int64_t)mb * 2 * 2 * 2048;
             for (int st = tde::kMaxStages; st >= 2; --st)
                 if (fixed + st * chunk <= kSmemLimit) {
@@ -638,15 +638,31 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
         t.x = x; t.B = n_points; t.n_tiles = g.tc_tiles;
         t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb; t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc;
         { const char* d = getenv("TDE_TC_DBG"); t.dbg = d ? atoi(d) : 0; }
+        static long long* dbg_buf = nullptr;
+        if (t.dbg & 4) {
+            if (!dbg_buf) { cudaMalloc(&dbg_buf, 16 * sizeof(long long)); cudaMemset(dbg_buf, 0, 16 * sizeof(long long)); }
+            t.dbg_buf = dbg_buf;
+        }
         for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
         t.w_in = ws + g.o_w_in; t.b_in = ws + g.o_b_in; t.wc = ws + g.o_wc; t.b_hidden = ws + g.o_bh;
         t.w_out = ws + g.o_wo; t.b_out = ws + g.o_bo;
         t.out = out; t.ld_out = ld_out; t.stash = stash;
         t.stash_layer_stride = g.n_tiles * g.W * (int64_t)g.TP * g.J;
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
-        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), g.tc_tiles));
-        ScopedTimer timer(st, 0);
-        TDE_CUDA(g.disp->fwd_tc(t, grid, g.tc_smem, st));
+        // clusters of kTcCluster CTAs: even grid, never more clusters than tile pairs
+        const int64_t pairs = (g.tc_tiles + tde::kTcCluster - 1) / tde::kTcCluster;
+        const int grid = (int)(tde::kTcCluster * std::max<int64_t>(1, std::min<int64_t>(sm_count() / tde::kTcCluster, pairs)));
+        {
+            ScopedTimer timer(st, 0);
+            TDE_CUDA(g.disp->fwd_tc(t, grid, g.tc_smem, st));
+        }
+        if (t.dbg & 4) {
+            long long h[16];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, dbg_buf, sizeof h, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[tc dbg] epi: wait_acc %lld  tmem_ld %lld  math+sts %lld  stash %lld  publish %lld | mma: wait_act %lld  issue+commit %lld | epi_start-to-mma_done %lld\n",
+                    h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[9] - h[8], h[10] - h[9], h[10] - h[0]);
+        }
     } else {
         tde::JetParams p;
         fill_params(g, spec, ws, &p);
