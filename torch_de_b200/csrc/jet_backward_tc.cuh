@@ -1,0 +1,535 @@
+// tcgen05 reverse sweep for wide layers (W = 128 or 256), two kernels:
+//
+//  jet_backward_tc_kernel : seeds -> Hbar jets of every layer.  The dX GEMMs  Zbar_{l-1}[k][col] = sum_n W_l[n][k] Hbar_l[n][col]
+//      run on the tensor cores exactly like the forward (A = W_l^T image streamed + multicast, B = Hbar planes resident in
+//      smem, D in TMEM with lane = neuron, 3xTF32).  The epilogue thread owns one neuron for all 16 points of the tile, so
+//      the activation adjoint, the bias gradients, dW_out and dW_in need no cross-thread reduction at all.  It also writes
+//      Hbar_l and Z_l to HBM ([layer][tile][column][neuron], coalesced) for the weight-gradient kernel.
+//
+//  jet_dw_tc_kernel       : dW_l[n][k] = sum_{points, channels} Hbar_l[n][col] * Z_{l-1}[k][col]  as a split-K tensor-core GEMM
+//      (M = n, N = k = 256 TMEM columns per neuron block, K = jet columns).  Loader threads read the two FP32 streams
+//      coalesced, split them 3xTF32 and lay them out as K-major UMMA core matrices; the accumulator is flushed to the CTA's
+//      private gradient slab every few tiles (FP32 RED, single writer) so the tensor core's round-toward-zero accumulation
+//      never runs long enough to bias the gradient.
+#pragma once
+#include "jet_forward_tc.cuh"
+
+namespace tde {
+
+struct TcBwdParams {
+    const float* x;
+    int64_t B;
+    int64_t n_tiles;            // 16-point tiles
+    int d_in, n_out, L, W, act, MB;
+    int n_stages, n_acc;
+    int first_in[TDE_MAX_FIRST];
+    const float* wct;           // transposed-weight chunk images [(L-1)][W/8][chunk]
+    const float* w_out;         // [n_out][W] packed
+    const float* seeds;
+    int64_t ld_seeds;
+    const float* stash;         // forward stash (t | h_c)   [L][bw tiles][cols][W]
+    float* hbar;                // Hbar_l                    same layout (layers 1..L-1 used)
+    float* zst;                 // Z_l                       same layout (layers 0..L-2 used)
+    int64_t stash_layer_stride;
+    int tiles_per_bw_tile;
+    float* gpart;               // per-CTA slabs
+    int64_t gp_stride, gp_off_b_in, gp_off_b_hidden, gp_off_w_out, gp_off_b_out;
+};
+
+__device__ __forceinline__ void slab_add(float* dst, float v, bool first) {
+    if (first) {
+        *dst = v;
+    } else {
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(v) : "memory");
+    }
+}
+
+template <int NF, int SMASK>
+__global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __grid_constant__ TcBwdParams p) {
+    using S = JetSpecT<NF, SMASK>;
+    constexpr int J = S::J;
+    constexpr int N = kTcPoints * J;
+    constexpr uint32_t ATOMK = (N / 8) * 1024;
+    extern __shared__ __align__(1024) unsigned char smem_tc[];
+    unsigned char* const smem_raw = smem_tc;
+
+    const int W = p.W, MB = p.MB;
+    const int n_stages = p.n_stages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* act_ready = empty + kMaxStages;
+    uint64_t* acc_ready = act_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+    unsigned char* zhi = smem_raw + 1024;
+    const uint32_t z_plane = (uint32_t)(W / 32) * ATOMK;
+    unsigned char* zlo = zhi + z_plane;
+    const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;
+    unsigned char* wst = zlo + z_plane;
+    float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
+    float* xs = wout_s + p.n_out * W;                 // [16][d_in]
+    float* seeds_s = xs + kTcPoints * p.d_in;         // [J*n_out][16]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_epi_warps = 4 * MB;
+    const int n_epi = 128 * MB;
+    const int n_ks = W / kTcKC;
+
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kTcCluster);
+        }
+        mbar_init(act_ready, n_epi_warps);
+        mbar_init(acc_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = cluster_ctarank();
+    const int64_t n_pairs = (p.n_tiles + kTcCluster - 1) / kTcCluster;
+    const int64_t first_pair = blockIdx.x / kTcCluster, pair_step = gridDim.x / kTcCluster;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid == 0) {
+            // ===== producer: W_l^T chunk images, layers L-1 .. 1 =====
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t part = chunk_bytes / kTcCluster;
+            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
+                for (int l = p.L - 1; l >= 1; --l) {
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wct) + (size_t)(l - 1) * n_ks * chunk_bytes;
+                    for (int ks = 0; ks < n_ks; ++ks) {
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_expect_tx(&full[s], chunk_bytes);
+                        bulk_g2s_mc(wst + (size_t)s * chunk_bytes + crank * part, src + (size_t)ks * chunk_bytes + crank * part, part,
+                                    &full[s], (uint16_t)((1u << kTcCluster) - 1));
+                        if (++s == n_stages) {
+                            s = 0;
+                            ph ^= 1;
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer (warp converged, one elected lane) =====
+            const bool leader = elect_one();
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t b_hi0 = umma_desc_sw128(smem_u32(zhi), 1024);
+            const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
+            const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
+            const uint32_t stage_step = chunk_bytes >> 4, blk_step = 4096u >> 4;
+            const int n_acc = p.n_acc;
+            int s = 0;
+            uint32_t ph = 0, act_ph = 0;
+            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
+                for (int l = p.L - 1; l >= 1; --l) {
+                    mbar_wait(act_ready, act_ph);   // Hbar_l planes written, accumulators drained
+                    act_ph ^= 1;
+                    tc_fence_after();
+                    for (int ks = 0; ks < n_ks; ++ks) {
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t koff = ((uint32_t)(ks >> 2) * ATOMK + (uint32_t)(ks & 3) * 32u) >> 4;
+                            const uint64_t b_hi = b_hi0 + (uint64_t)koff;
+                            const uint64_t b_lo = b_lo0 + (uint64_t)koff;
+                            const uint64_t a_stage = a0 + (uint64_t)(s * stage_step);
+                            const uint32_t main_set = n_acc == 3 ? (uint32_t)(1 + (ks & 1)) : (n_acc == 2 ? 1u : 0u);
+                            const uint32_t acc_main = n_acc == 3 ? (uint32_t)(ks >= 2) : (n_acc == 2 ? (uint32_t)(ks > 0) : 1u);
+                            for (int mb = 0; mb < MB; ++mb) {
+                                const uint64_t a_hi = a_stage + (uint64_t)(mb * blk_step);
+                                const uint64_t a_lo = a_stage + (uint64_t)((MB + mb) * blk_step);
+                                const uint32_t d_small = tmem_base + (uint32_t)(mb * N);
+                                const uint32_t d_main = tmem_base + (uint32_t)((main_set * MB + mb) * N);
+                                umma_tf32(d_small, a_lo, b_hi, idesc, ks > 0);
+                                umma_tf32(d_small, a_hi, b_lo, idesc, 1);
+                                umma_tf32(d_main, a_hi, b_hi, idesc, acc_main);
+                            }
+                            umma_commit_mc(&empty[s], (uint16_t)((1u << kTcCluster) - 1));
+                        }
+                        __syncwarp();
+                        if (++s == n_stages) {
+                            s = 0;
+                            ph ^= 1;
+                        }
+                    }
+                    if (leader) umma_commit(acc_ready);
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+        const int e = warp - 4;
+        if (e < n_epi_warps) {
+            const int quarter = warp & 3;
+            const int mb = e >> 2;
+            const int n = mb * 128 + quarter * 32 + lane;   // the neuron this thread owns (in every layer)
+            const int et = e * 32 + lane;
+            auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory"); };
+
+            for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
+            const uint32_t zrow = (uint32_t)(n >> 5) * ATOMK + (uint32_t)(n & 3) * 4u;
+            const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;
+            float* gp = p.gpart + (size_t)blockIdx.x * p.gp_stride;
+            uint32_t acc_ph = 0;
+
+            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
+                const bool first = pair == first_pair;
+                const int64_t tile = pair * kTcCluster + crank;
+                const bool real = tile < p.n_tiles;
+                const int64_t pbase = tile * kTcPoints;
+                for (int i = et; i < kTcPoints * p.d_in; i += n_epi) {
+                    const int64_t gpt = pbase + i / p.d_in;
+                    xs[i] = gpt < p.B ? p.x[gpt * p.d_in + (i % p.d_in)] : 0.0f;
+                }
+                for (int i = et; i < J * p.n_out * kTcPoints; i += n_epi) {
+                    const int r = i / kTcPoints, pt = i - r * kTcPoints;
+                    const int64_t gpt = pbase + pt;
+                    seeds_s[i] = gpt < p.B ? p.seeds[(size_t)r * p.ld_seeds + gpt] : 0.0f;
+                }
+                epi_sync();
+                size_t row0 = 0;
+                if (real) {
+                    const int64_t bw_tile = tile / p.tiles_per_bw_tile;
+                    const int sub = (int)(tile - bw_tile * p.tiles_per_bw_tile);
+                    row0 = ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N) * W + n;
+                }
+
+                float g[N];   // Zbar of the current layer (then reused)
+                float dwo[TDE_MAX_OUT];
+#pragma unroll
+                for (int o = 0; o < TDE_MAX_OUT; ++o) dwo[o] = 0.0f;
+                {
+                    float wo[TDE_MAX_OUT];
+#pragma unroll
+                    for (int o = 0; o < TDE_MAX_OUT; ++o) wo[o] = o < p.n_out ? wout_s[o * W + n] : 0.0f;
+#pragma unroll
+                    for (int pt = 0; pt < kTcPoints; ++pt)
+#pragma unroll
+                        for (int c = 0; c < J; ++c) {
+                            float a = 0.0f;
+#pragma unroll
+                            for (int o = 0; o < TDE_MAX_OUT; ++o)
+                                if (o < p.n_out) a = fmaf(wo[o], seeds_s[(c * p.n_out + o) * kTcPoints + pt], a);
+                            g[pt * J + c] = a;
+                        }
+                }
+
+                for (int l = p.L - 1; l >= 0; --l) {
+                    if (l < p.L - 1) {
+                        mbar_wait(acc_ready, acc_ph);
+                        acc_ph ^= 1;
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
+#pragma unroll
+                        for (int c0 = 0; c0 < N; c0 += 16) tmem_ld16(taddr + c0, g + c0);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        for (int a = 1; a < p.n_acc; ++a) {
+#pragma unroll
+                            for (int c0 = 0; c0 < N; c0 += 16) {
+                                float part[16];
+                                tmem_ld16(taddr + (uint32_t)(a * MB * N) + c0, part);
+                                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) g[c0 + i] += part[i];
+                            }
+                        }
+                    }
+                    const float* srow = p.stash + (size_t)l * p.stash_layer_stride + row0;
+                    float* hrow = p.hbar + (size_t)l * p.stash_layer_stride + row0;
+                    float* zrow_g = p.zst + (size_t)l * p.stash_layer_stride + row0;
+                    const bool last = l == p.L - 1;
+                    float db = 0.0f;
+                    float dw_in[TDE_MAX_IN];
+#pragma unroll
+                    for (int i = 0; i < TDE_MAX_IN; ++i) dw_in[i] = 0.0f;
+#pragma unroll
+                    for (int pt = 0; pt < kTcPoints; ++pt) {
+                        float st[J], zb[J], hb[J], z[J];
+#pragma unroll
+                        for (int c = 0; c < J; ++c) {
+                            st[c] = real ? __ldcs(srow + (size_t)(pt * J + c) * W) : 0.0f;
+                            zb[c] = g[pt * J + c];
+                        }
+                        act_backward<S, true>(p.act, st, zb, hb, z);
+                        db += hb[0];
+                        if (last) {
+#pragma unroll
+                            for (int c = 0; c < J; ++c)
+#pragma unroll
+                                for (int o = 0; o < TDE_MAX_OUT; ++o)
+                                    if (o < p.n_out) dwo[o] = fmaf(seeds_s[(c * p.n_out + o) * kTcPoints + pt], z[c], dwo[o]);
+                        }
+                        if (l >= 1) {
+#pragma unroll
+                            for (int c = 0; c < J; ++c) {
+                                const int col = pt * J + c;
+                                if (real) __stcs(hrow + (size_t)col * W, hb[c]);
+                                const uint32_t off = zrow + (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u +
+                                                     ((kchunk ^ (uint32_t)(col & 7)) << 4);
+                                float hi, lo;
+                                split_tf32(hb[c], hi, lo);
+                                *reinterpret_cast<float*>(zhi + off) = hi;
+                                *reinterpret_cast<float*>(zlo + off) = lo;
+                            }
+                        } else {
+                            // input layer: h = W0 x + b0, h_a = W0[:, first_in[a]]
+                            const float h0 = hb[0];
+#pragma unroll
+                            for (int i = 0; i < TDE_MAX_IN; ++i)
+                                if (i < p.d_in) dw_in[i] = fmaf(h0, xs[pt * p.d_in + i], dw_in[i]);
+#pragma unroll
+                            for (int a = 0; a < NF; ++a) {
+#pragma unroll
+                                for (int i = 0; i < TDE_MAX_IN; ++i)
+                                    if (i == p.first_in[a]) dw_in[i] += hb[1 + a];
+                            }
+                        }
+                        if (l <= p.L - 2 && real) {
+#pragma unroll
+                            for (int c = 0; c < J; ++c) __stcs(zrow_g + (size_t)(pt * J + c) * W, z[c]);
+                        }
+                    }
+                    if (l >= 1) {
+                        fence_proxy_async();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(act_ready);
+                        slab_add(gp + p.gp_off_b_hidden + (size_t)(l - 1) * W + n, db, first);
+                    } else {
+                        slab_add(gp + p.gp_off_b_in + n, db, first);
+#pragma unroll
+                        for (int i = 0; i < TDE_MAX_IN; ++i)
+                            if (i < p.d_in) slab_add(gp + (size_t)n * p.d_in + i, dw_in[i], first);
+                    }
+                    if (last) {
+#pragma unroll
+                        for (int o = 0; o < TDE_MAX_OUT; ++o)
+                            if (o < p.n_out) slab_add(gp + p.gp_off_w_out + (size_t)o * W + n, dwo[o], first);
+                    }
+                }
+                if (et < p.n_out) {
+                    float s = 0.0f;
+                    for (int pt = 0; pt < kTcPoints; ++pt) s += seeds_s[(size_t)et * kTcPoints + pt];   // channel-0 rows come first
+                    slab_add(gp + p.gp_off_b_out + et, s, first);
+                }
+                epi_sync();   // xs / seeds_s are rewritten by the next tile
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dW_l = Hbar_l^T-contract Z_{l-1} on the tensor cores
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kDwThreads = 384;       // warp 1: MMA issuer, warps 4..11: loaders / flushers (one thread per neuron)
+constexpr int kDwStages = 6;          // operand stages, one 8-column k-step each
+constexpr int kDwFlushTiles = 8;      // accumulator is flushed to the slab after this many 16-point tiles
+
+struct TcDwParams {
+    int64_t n_tiles;                  // 16-point tiles
+    int L, W, MB, J;
+    const float* hbar;                // [L][bw tiles][cols][W]
+    const float* zst;
+    int64_t stash_layer_stride;
+    int tiles_per_bw_tile;
+    float* gpart;                     // per-CTA slabs; hidden dW of layer l at gp_off_hidden + (l-1)*W*W, [n][k]
+    int64_t gp_stride, gp_off_hidden;
+};
+
+template <int UNUSED>
+__global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_constant__ TcDwParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_tc[];
+    unsigned char* const smem_raw = smem_tc;
+    const int W = p.W, MB = p.MB;
+    const int N = 16 * p.J;                       // jet columns per tile
+    const int n_ks = N / 8;                       // k-steps per tile
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);       // [kDwStages] loaders -> MMA (count = loader warps)
+    uint64_t* empty = full + kDwStages;                            // MMA -> loaders (tcgen05.commit)
+    uint64_t* acc_done = empty + kDwStages;                        // MMA -> flushers
+    uint64_t* acc_free = acc_done + 1;                             // flushers -> MMA (count = loader warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+    // stage: A_hi | A_lo | B_hi | B_lo, each W rows x 8 k as K-major SWIZZLE_NONE core matrices: [kgroup 2][W/8 row groups][8][4]
+    const uint32_t op_bytes = (uint32_t)W * 8u * 4u;
+    const uint32_t stage_bytes = 4u * op_bytes;
+    unsigned char* stages = smem_raw + 1024;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_ld_warps = 4 * MB;
+    if (tid == 0) {
+        for (int s = 0; s < kDwStages; ++s) {
+            mbar_init(&full[s], n_ld_warps);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_done, 1);
+        mbar_init(acc_free, n_ld_warps);
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tiles of this CTA: blockIdx.x, + gridDim.x, ...   (every CTA has at least one)
+    const int64_t my_tiles = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp == 1) {
+            const bool leader = elect_one();
+            // D = F32, A = B = TF32 K-major, N = W (k neurons), M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(W >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t lbo = (uint32_t)(W / 8) * 128u;        // bytes between the two k-groups
+            const uint64_t d0 = umma_desc(smem_u32(stages), lbo, 128);
+            int s = 0;
+            uint32_t ph = 0, free_ph = 0;
+            for (int l = 1; l < p.L; ++l) {
+                for (int64_t t0 = 0; t0 < my_tiles; t0 += kDwFlushTiles) {
+                    const int64_t t1 = t0 + kDwFlushTiles < my_tiles ? t0 + kDwFlushTiles : my_tiles;
+                    mbar_wait(acc_free, free_ph ^ 1);    // the previous flush has drained TMEM (passes immediately the first time)
+                    free_ph ^= 1;
+                    tc_fence_after();
+                    uint32_t accum = 0;
+                    for (int64_t t = t0; t < t1; ++t) {
+                        for (int ks = 0; ks < n_ks; ++ks) {
+                            mbar_wait(&full[s], ph);
+                            tc_fence_after();
+                            if (leader) {
+                                const uint64_t st = d0 + (uint64_t)((uint32_t)s * (stage_bytes >> 4));
+                                const uint64_t a_hi = st, a_lo = st + (uint64_t)(op_bytes >> 4);
+                                const uint64_t b_hi = st + (uint64_t)(2 * (op_bytes >> 4)), b_lo = st + (uint64_t)(3 * (op_bytes >> 4));
+                                for (int mb = 0; mb < MB; ++mb) {
+                                    const uint64_t aoff = (uint64_t)(mb * ((16u * 128u) >> 4));   // 128 rows = 16 row groups further
+                                    const uint32_t d = tmem_base + (uint32_t)(mb * W);
+                                    umma_tf32(d, a_lo + aoff, b_hi, idesc, accum);
+                                    umma_tf32(d, a_hi + aoff, b_lo, idesc, 1);
+                                    umma_tf32(d, a_hi + aoff, b_hi, idesc, 1);
+                                }
+                                umma_commit(&empty[s]);
+                            }
+                            accum = 1;
+                            __syncwarp();
+                            if (++s == kDwStages) {
+                                s = 0;
+                                ph ^= 1;
+                            }
+                        }
+                    }
+                    if (leader) umma_commit(acc_done);
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+        const int e = warp - 4;
+        if (e < n_ld_warps) {
+            const int quarter = warp & 3;
+            const int mb = e >> 2;
+            const int n = mb * 128 + quarter * 32 + lane;    // neuron loaded by this thread; TMEM lane it flushes
+            float* gp = p.gpart + (size_t)blockIdx.x * p.gp_stride + p.gp_off_hidden;
+            // byte offset of row n inside an operand block: [kgroup][row group][row][4 k]
+            const uint32_t rowoff = (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u;
+            const uint32_t lbo = (uint32_t)(W / 8) * 128u;
+            int s = 0;
+            uint32_t ph = 0, done_ph = 0;
+            bool first_flush_of_layer;
+            for (int l = 1; l < p.L; ++l) {
+                first_flush_of_layer = true;
+                const float* hsrc = p.hbar + (size_t)l * p.stash_layer_stride;
+                const float* zsrc = p.zst + (size_t)(l - 1) * p.stash_layer_stride;
+                for (int64_t t0 = 0; t0 < my_tiles; t0 += kDwFlushTiles) {
+                    const int64_t t1 = t0 + kDwFlushTiles < my_tiles ? t0 + kDwFlushTiles : my_tiles;
+                    for (int64_t t = t0; t < t1; ++t) {
+                        const int64_t tile = blockIdx.x + t * gridDim.x;
+                        const int64_t bw_tile = tile / p.tiles_per_bw_tile;
+                        const int sub = (int)(tile - bw_tile * p.tiles_per_bw_tile);
+                        const size_t row0 = ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N) * W + n;
+                        for (int ks = 0; ks < n_ks; ++ks) {
+                            float hv[8], zv[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                hv[c] = __ldcs(hsrc + row0 + (size_t)(ks * 8 + c) * W);
+                                zv[c] = __ldcs(zsrc + row0 + (size_t)(ks * 8 + c) * W);
+                            }
+                            mbar_wait(&empty[s], ph ^ 1);
+                            unsigned char* st = stages + (size_t)s * stage_bytes;
+#pragma unroll
+                            for (int kg = 0; kg < 2; ++kg) {
+                                float4 hh, hl, zh, zl;
+                                split_tf32(hv[4 * kg + 0], hh.x, hl.x);
+                                split_tf32(hv[4 * kg + 1], hh.y, hl.y);
+                                split_tf32(hv[4 * kg + 2], hh.z, hl.z);
+                                split_tf32(hv[4 * kg + 3], hh.w, hl.w);
+                                split_tf32(zv[4 * kg + 0], zh.x, zl.x);
+                                split_tf32(zv[4 * kg + 1], zh.y, zl.y);
+                                split_tf32(zv[4 * kg + 2], zh.z, zl.z);
+                                split_tf32(zv[4 * kg + 3], zh.w, zl.w);
+                                const uint32_t o = (uint32_t)kg * lbo + rowoff;
+                                *reinterpret_cast<float4*>(st + o) = hh;
+                                *reinterpret_cast<float4*>(st + op_bytes + o) = hl;
+                                *reinterpret_cast<float4*>(st + 2 * op_bytes + o) = zh;
+                                *reinterpret_cast<float4*>(st + 3 * op_bytes + o) = zl;
+                            }
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&full[s]);
+                            if (++s == kDwStages) {
+                                s = 0;
+                                ph ^= 1;
+                            }
+                        }
+                    }
+                    // ---- flush the accumulator rows of this thread's neuron into the slab ----
+                    mbar_wait(acc_done, done_ph);
+                    done_ph ^= 1;
+                    tc_fence_after();
+                    float* dst = gp + (size_t)(l - 1) * W * W + (size_t)n * W;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * W);
+                    for (int c0 = 0; c0 < W; c0 += 16) {
+                        float v[16];
+                        tmem_ld16(taddr + c0, v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            if (first_flush_of_layer) {
+                                *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            } else {
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + i), "f"(v[i]), "f"(v[i + 1]),
+                                             "f"(v[i + 2]), "f"(v[i + 3])
+                                             : "memory");
+                            }
+                        }
+                    }
+                    first_flush_of_layer = false;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_free);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+}  // namespace tde

@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     // activation planes: K-major SWIZZLE_128B atoms of 8 jet columns x 32 k (1024 B), ordered [k/32][col/8].  A warp's 32
     // consecutive neurons write one full 128 B row per column (conflict-free) and every MMA operand row is 128 B aligned.
     constexpr uint32_t ATOMK = (N / 8) * 1024;   // bytes between k-atoms
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_tc[];
+    unsigned char* const smem_raw = smem_tc;
 
     const int W = p.W, MB = p.MB;
     const int n_stages = p.n_stages;

@@ -2,6 +2,7 @@
 #pragma once
 #include "jet_common.cuh"
 #include "jet_forward_tc.cuh"
+#include "jet_backward_tc.cuh"
 
 // (NF, SMASK) list. SMASK bits enumerate pairs (0,0),(0,1),..,(1,1),.. over the NF first-order channels.
 #define TDE_SPEC_LIST(X) \
@@ -19,10 +20,12 @@
 namespace tde {
 typedef cudaError_t (*JetLauncher)(const JetParams&, int grid, int smem, cudaStream_t);
 typedef cudaError_t (*TcLauncher)(const TcParams&, int grid, int smem, cudaStream_t);
+typedef cudaError_t (*TcBwdLauncher)(const TcBwdParams&, int grid, int smem, cudaStream_t);
 #define TDE_DECL(nf, sm)                                                                  \
     cudaError_t launch_forward_##nf##_##sm(const JetParams&, int, int, cudaStream_t);     \
     cudaError_t launch_backward_##nf##_##sm(const JetParams&, int, int, cudaStream_t);     \
-    cudaError_t launch_forward_tc_##nf##_##sm(const TcParams&, int, int, cudaStream_t);
+    cudaError_t launch_forward_tc_##nf##_##sm(const TcParams&, int, int, cudaStream_t);   \
+    cudaError_t launch_backward_tc_##nf##_##sm(const TcBwdParams&, int, int, cudaStream_t);
 TDE_SPEC_LIST(TDE_DECL)
 #undef TDE_DECL
 }  // namespace tde

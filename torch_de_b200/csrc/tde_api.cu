@@ -66,8 +66,9 @@ struct Dispatch {
     int nf, smask;
     tde::JetLauncher fwd, bwd;
     tde::TcLauncher fwd_tc;
+    tde::TcBwdLauncher bwd_tc;
 };
-#define TDE_ROW(nf, sm) {nf, sm, tde::launch_forward_##nf##_##sm, tde::launch_backward_##nf##_##sm, tde::launch_forward_tc_##nf##_##sm},
+#define TDE_ROW(nf, sm) {nf, sm, tde::launch_forward_##nf##_##sm, tde::launch_backward_##nf##_##sm, tde::launch_forward_tc_##nf##_##sm, tde::launch_backward_tc_##nf##_##sm},
 const Dispatch kDispatch[] = {TDE_SPEC_LIST(TDE_ROW)};
 #undef TDE_ROW
 
@@ -91,6 +92,8 @@ struct Geometry {
     int64_t o_w_in, o_b_in, o_wt, o_wn, o_bh, o_wo, o_bo, o_wc, packed_floats;
     // tcgen05 forward (wide layers)
     int use_tc, tc_mb, tc_stages, tc_smem, tc_nacc;
+    int use_tc_bwd, dw_smem;
+    int64_t o_wct, o_hbar, o_zst, grid_b1, grid_b2;
     int64_t tc_tiles;
     // per-CTA partial gradient slab
     int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo, gp_stride;
@@ -240,6 +243,16 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     }
     o = align_up(o, 64);
     g.o_wc = o;   if (g.use_tc) o += (int64_t)(L - 1) * 2 * WW;
+    g.use_tc_bwd = 0;
+    {
+        const char* no_b = getenv("TDE_NO_TC_BWD");
+        g.dw_smem = 1024 + tde::kDwStages * 4 * g.W * 32;
+        if (g.use_tc && g.dw_smem <= kSmemLimit && !(no_b && no_b[0] == '1')) {
+            g.use_tc_bwd = 1;
+            g.rsplit = 1;      // the FFMA dW phase (and its column split) is not used on this path
+        }
+    }
+    g.o_wct = o;  if (g.use_tc_bwd) o += (int64_t)(L - 1) * 2 * WW;
     g.packed_floats = align_up(o, 64);
 
     int64_t q = 0;
@@ -251,8 +264,17 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.g_bo = q;     q = align_up(q + g.n_out, 4);
     g.gp_stride = q;
     g.o_gpart = g.packed_floats;
-    g.workspace_floats = g.packed_floats + (int64_t)g.n_ctas * g.gp_stride;
     g.stash_floats = (int64_t)L * g.n_tiles * g.W * g.TP * g.J;
+    g.workspace_floats = align_up(g.packed_floats + (int64_t)std::max(g.n_ctas, sm_count()) * g.gp_stride, 64);
+    g.o_hbar = g.o_zst = 0;
+    if (g.use_tc_bwd) {       // Hbar_l and Z_l streams for the tensor-core weight-gradient kernel
+        g.o_hbar = g.workspace_floats;
+        g.o_zst = g.o_hbar + g.stash_floats;
+        g.workspace_floats = g.o_zst + g.stash_floats;
+        const int64_t pairs = (g.tc_tiles + tde::kTcCluster - 1) / tde::kTcCluster;
+        g.grid_b1 = tde::kTcCluster * std::max<int64_t>(1, std::min<int64_t>(sm_count() / tde::kTcCluster, pairs));
+        g.grid_b2 = std::max<int64_t>(1, std::min<int64_t>(sm_count(), g.tc_tiles));
+    }
 
     int64_t np = 0;
     for (int l = 0; l < net->n_layers; ++l)
@@ -320,7 +342,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* _
 
 // tcgen05 operand image of the hidden weights: per layer, per 8-k chunk: [hi|lo][neuron block][k group of 4][16 row
 // groups][8 rows][4 k] -- exactly the shared-memory layout of the K-major SWIZZLE_NONE UMMA A operand, split 3xTF32.
-__global__ void pack_tc_weights_kernel(const __grid_constant__ PackArgs a, float* __restrict__ wc, int MB) {
+__global__ void pack_tc_weights_kernel(const __grid_constant__ PackArgs a, float* __restrict__ wc, int MB, int transpose) {
     const int W = a.W;
     const int64_t per_layer = 2LL * W * W;
     const int64_t total = (int64_t)(a.L - 1) * per_layer;
@@ -337,7 +359,8 @@ __global__ void pack_tc_weights_kernel(const __grid_constant__ PackArgs a, float
         const int rr = c / 4, kk = c % 4;
         const int n = mb * 128 + rg * 8 + rr, k = ks * 8 + kg * 4 + kk;
         float v = 0.0f;
-        if (n < a.width && k < a.width) v = a.net.layers[l].weight[(int64_t)n * a.width + k];
+        if (n < a.width && k < a.width)
+            v = transpose ? a.net.layers[l].weight[(int64_t)k * a.width + n] : a.net.layers[l].weight[(int64_t)n * a.width + k];
         float hi, lo;
         tde::split_tf32(v, hi, lo);
         wc[i] = hl ? lo : hi;
@@ -357,7 +380,12 @@ int launch_pack(const TdeNet* net, const Geometry& g, float* ws, bool want_wt, b
     ++g_launches;
     TDE_CUDA(cudaGetLastError());
     if (want_wt && g.use_tc) {
-        pack_tc_weights_kernel<<<148 * 4, threads, 0, st>>>(a, ws + g.o_wc, g.tc_mb);
+        pack_tc_weights_kernel<<<148 * 4, threads, 0, st>>>(a, ws + g.o_wc, g.tc_mb, 0);
+        ++g_launches;
+        TDE_CUDA(cudaGetLastError());
+    }
+    if (want_wn && g.use_tc_bwd) {
+        pack_tc_weights_kernel<<<148 * 4, threads, 0, st>>>(a, ws + g.o_wct, g.tc_mb, 1);
         ++g_launches;
         TDE_CUDA(cudaGetLastError());
     }
@@ -381,7 +409,7 @@ void fill_params(const Geometry& g, const TdeJetSpec* spec, float* ws, tde::JetP
 // second-stage reduction: flat_grad[i] += scale * sum_{cta (, split)} slab[cta][map(i)]   (fixed order)
 // ---------------------------------------------------------------------------------------------
 struct ReduceArgs {
-    int n_layers, W, width, d_in, n_out, rsplit, n_active;
+    int n_layers, W, width, d_in, n_out, rsplit, n_active, n_active_hidden;
     int64_t n_params, gp_stride;
     int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo;
     float scale;
@@ -428,7 +456,8 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
         }
     }
     float s = 0.0f;
-    for (int c = 0; c < a.n_active; ++c) {
+    const int n_slabs = splits > 1 || src >= a.g_hidden && src < a.g_bh ? a.n_active_hidden : a.n_active;
+    for (int c = 0; c < n_slabs; ++c) {
         const float* slab = gpart + (int64_t)c * a.gp_stride + src;
         for (int q = 0; q < splits; ++q) s += slab[(int64_t)q * WW];
     }
@@ -685,18 +714,51 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = (float*)workspace;
     if (int rc = launch_pack(net, g, ws, false, true, st)) return rc;
-    tde::JetParams p;
-    fill_params(g, spec, ws, &p);
-    p.x = x; p.B = n_points; p.stash = const_cast<float*>(stash); p.seeds = seeds; p.ld_seeds = ld_seeds;
-    p.n_stages = g.stages_bwd;
-    {
-        ScopedTimer timer(st, 1);
-        TDE_CUDA(g.disp->bwd(p, g.n_ctas, g.smem_bwd, st));
+    int n_active = g.n_ctas, n_active_hidden = g.n_ctas;
+    if (g.use_tc_bwd) {
+        tde::TcBwdParams t{};
+        t.x = x; t.B = n_points; t.n_tiles = g.tc_tiles;
+        t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb;
+        t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc;
+        for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
+        t.wct = ws + g.o_wct; t.w_out = ws + g.o_wo;
+        t.seeds = seeds; t.ld_seeds = ld_seeds; t.stash = stash;
+        t.hbar = ws + g.o_hbar; t.zst = ws + g.o_zst;
+        t.stash_layer_stride = g.n_tiles * g.W * (int64_t)g.TP * g.J;
+        t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
+        t.gpart = ws + g.o_gpart; t.gp_stride = g.gp_stride;
+        t.gp_off_b_in = g.g_b_in; t.gp_off_b_hidden = g.g_bh; t.gp_off_w_out = g.g_wo; t.gp_off_b_out = g.g_bo;
+        tde::TcDwParams d{};
+        d.n_tiles = g.tc_tiles; d.L = g.L; d.W = g.W; d.MB = g.tc_mb; d.J = g.J;
+        d.hbar = t.hbar; d.zst = t.zst; d.stash_layer_stride = t.stash_layer_stride; d.tiles_per_bw_tile = t.tiles_per_bw_tile;
+        d.gpart = t.gpart; d.gp_stride = g.gp_stride; d.gp_off_hidden = g.g_hidden;
+        {
+            ScopedTimer timer(st, 1);
+            TDE_CUDA(g.disp->bwd_tc(t, (int)g.grid_b1, g.tc_smem, st));
+            if (g.L >= 2) {
+                auto k = tde::jet_dw_tc_kernel<0>;
+                TDE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g.dw_smem));
+                k<<<(int)g.grid_b2, tde::kDwThreads, g.dw_smem, st>>>(d);
+                TDE_CUDA(cudaGetLastError());
+            }
+        }
+        g_launches += 3;
+        n_active = (int)g.grid_b1;
+        n_active_hidden = (int)g.grid_b2;
+    } else {
+        tde::JetParams p;
+        fill_params(g, spec, ws, &p);
+        p.x = x; p.B = n_points; p.stash = const_cast<float*>(stash); p.seeds = seeds; p.ld_seeds = ld_seeds;
+        p.n_stages = g.stages_bwd;
+        {
+            ScopedTimer timer(st, 1);
+            TDE_CUDA(g.disp->bwd(p, g.n_ctas, g.smem_bwd, st));
+        }
+        g_launches += 2;  // reverse sweep + second-stage reduction
     }
-    g_launches += 2;  // reverse sweep + second-stage reduction
     ReduceArgs r{};
     r.n_layers = net->n_layers; r.W = g.W; r.width = g.width; r.d_in = g.d_in; r.n_out = g.n_out;
-    r.rsplit = g.rsplit; r.n_active = g.n_ctas; r.n_params = g.n_params; r.gp_stride = g.gp_stride;
+    r.rsplit = g.rsplit; r.n_active = n_active; r.n_active_hidden = n_active_hidden; r.n_params = g.n_params; r.gp_stride = g.gp_stride;
     r.g_b_in = g.g_b_in; r.g_hidden = g.g_hidden; r.g_bh = g.g_bh; r.g_wo = g.g_wo; r.g_bo = g.g_bo;
     r.scale = grad_scale;
     const int threads = 256;

@@ -147,7 +147,7 @@ class JetRunner:
 # Largest activation stash kept from forward to backward, as a fraction of the free device memory at call
 # time.  Bigger batches switch to recompute mode: the forward keeps nothing and the backward re-runs the
 # forward chunk by chunk (+1/3 FLOPs, bounded memory) -- the cylinder config (2e6 pts/GPU x 10x512) needs it.
-STASH_FRACTION_OF_FREE = 0.35
+STASH_FRACTION_OF_FREE = 0.7
 
 
 class _JetFunction(torch.autograd.Function):
@@ -163,7 +163,8 @@ class _JetFunction(torch.autograd.Function):
                 free, _ = torch.cuda.mem_get_info(x.device)
                 free += torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
                 budget = STASH_FRACTION_OF_FREE * free
-                total = runner.plan(x.shape[0]).stash_bytes
+                # stash + workspace (the tensor-core backward keeps two more streams of the stash's size in the workspace)
+                total = runner.plan(x.shape[0]).stash_bytes + runner.plan(x.shape[0]).workspace_bytes
                 chunk = 0
                 if total > budget:
                     n_chunks = int(-(-total // budget))
