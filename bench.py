@@ -250,9 +250,7 @@ def run_ours(args, rank, local_rank, world):
     with ClockSampler(local_rank) as clk:
         ms_total = timed(args.steps, from_host=False)
     launches = lib.tde_launch_count() - launches0
-    fwd_ms, bwd_ms = C.c_double(), C.c_double()
-    n_fwd, n_bwd = C.c_int32(), C.c_int32()
-    lib.tde_profile_end(C.byref(fwd_ms), C.byref(n_fwd), C.byref(bwd_ms), C.byref(n_bwd))
+    lib.tde_profile_end(None, None, None, None)
 
     for _ in range(2):
         step(True).item()
@@ -264,26 +262,57 @@ def run_ours(args, rank, local_rank, world):
     value = n_pts_job * args.steps / (ms_total * 1e-3)
     e2e_value = n_pts_job * args.steps / (ms_e2e * 1e-3)
 
-    # roofline of the dominant kernel (reverse sweep: dX + dW = 4*J*sum(W_in*W_out) FLOP/pt)
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------
+    # algorithmic FLOPs: forward 2*J*sum(W_in*W_out) per point, reverse sweep (dX) 2*..., weight gradient
+    # (dW) 2*...; on the FFMA path dX and dW are one kernel.  achieved = FLOPs of all launches of that kernel in the timed
+    # region / its summed CUDA-event time (events recorded by the library right around each launch).
     peak = C.c_double()
     _lib.check(lib.tde_fp32_peak_probe(C.byref(peak), None), "tde_fp32_peak_probe")
-    J = runner.ch.n_channels
-    f_pt = wl.flops_per_point(J)
-    bwd_avg_ms = bwd_ms.value / max(1, n_bwd.value)
-    fwd_avg_ms = fwd_ms.value / max(1, n_fwd.value)
-    ach_bwd = (2.0 / 3.0) * f_pt * n_pts_rank / (bwd_avg_ms * 1e-3) * 1e-12
-    ach_fwd = (1.0 / 3.0) * f_pt * n_pts_rank / (fwd_avg_ms * 1e-3) * 1e-12
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     measured = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
-    roofline = {"bound": "fp32", "kernel": "jet_backward_kernel", "achieved": ach_bwd, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": ach_bwd / peak.value, "traffic": None,
-                "peak_source": "scalar-FFMA probe run in this process (tde_fp32_peak_probe); MEASURED_PEAKS.json has "
-                               "only HBM and bf16-tensor peaks and this kernel is FP32-FFMA bound",
-                "launch_ms": bwd_avg_ms, "share_of_step": bwd_ms.value / ms_total,
-                "forward_kernel": {"achieved": ach_fwd, "frac": ach_fwd / peak.value, "launch_ms": fwd_avg_ms,
-                                   "share_of_step": fwd_ms.value / ms_total},
-                "step_flops_frac_of_peak": f_pt * n_pts_rank * args.steps / (ms_total * 1e-3) * 1e-12 / peak.value,
-                "hbm_gbs_measured": measured.get("hbm_gbs"), "bf16_tflops_measured": measured.get("bf16_tflops")}
+    bf16_sustained = measured.get("bf16_tflops_sustained") or 1400.0
+    tensor_peak = bf16_sustained / 2.0 / 3.0            # TF32 = bf16/2; 3xTF32 issues 3 MMAs per FP32-accurate product
+    tensor_src = ("3xTF32 tensor roofline = MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 rate) / 3 (three MMAs per "
+                  "FP32-accurate product)" if measured else "fallback 1.4 PFLOP/s bf16 sustained / 2 / 3")
+    fp32_src = "scalar-FFMA probe run in this process (tde_fp32_peak_probe); MEASURED_PEAKS.json has no FP32 entry"
+    J = runner.ch.n_channels
+    f_pt = wl.flops_per_point(J)
+    plan = runner.plan(n_pts_rank)
+    paths = lib.tde_plan_paths(C.byref(runner._net), C.byref(runner._spec), n_pts_rank)
+    recompute = bool(runner.chunking and any(runner.chunking.values()))
+    pts_total = n_pts_rank * args.steps
+    ms, cnt = [], []
+    for k in range(3):
+        m, n = C.c_double(), C.c_int32()
+        lib.tde_profile_kind(k, C.byref(m), C.byref(n))
+        ms.append(m.value)
+        cnt.append(n.value)
+    kernels = []
+    fwd_flops = (1.0 / 3.0) * f_pt * pts_total * (2 if recompute else 1)
+    kernels.append(dict(kernel="jet_forward_tc_kernel" if paths & 1 else "jet_forward_kernel", flops=fwd_flops, ms=ms[0],
+                        launches=cnt[0], tensor=bool(paths & 1)))
+    if paths & 2:
+        kernels.append(dict(kernel="jet_backward_tc_kernel", flops=(1.0 / 3.0) * f_pt * pts_total, ms=ms[1], launches=cnt[1], tensor=True))
+        kernels.append(dict(kernel="jet_dw_tc_kernel", flops=(1.0 / 3.0) * f_pt * pts_total, ms=ms[2], launches=cnt[2], tensor=True))
+    else:
+        kernels.append(dict(kernel="jet_backward_kernel", flops=(2.0 / 3.0) * f_pt * pts_total, ms=ms[1], launches=cnt[1], tensor=False))
+    for k in kernels:
+        k["achieved"] = k["flops"] / (k["ms"] * 1e-3) * 1e-12 if k["ms"] > 0 else 0.0
+        k["bound"] = "tensor" if k["tensor"] else "fp32"
+        k["peak"] = tensor_peak if k["tensor"] else peak.value
+        k["frac"] = k["achieved"] / k["peak"]
+        k["launch_ms"] = k["ms"] / max(1, k["launches"])
+        k["share_of_step"] = k["ms"] / ms_total
+        del k["flops"], k["tensor"], k["ms"]
+    dom = max(kernels, key=lambda k: k["share_of_step"])
+    roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s",
+                "frac": dom["frac"], "traffic": None,
+                "peak_source": tensor_src if dom["bound"] == "tensor" else fp32_src,
+                "launch_ms": dom["launch_ms"], "share_of_step": dom["share_of_step"], "kernels": kernels,
+                "fp32_ffma_peak_probe": peak.value,
+                "step_fp32_equiv_tflops": f_pt * pts_total / (ms_total * 1e-3) * 1e-12,
+                "hbm_gbs_measured": measured.get("hbm_gbs"), "bf16_tflops_measured": measured.get("bf16_tflops"),
+                "bf16_tflops_sustained_measured": measured.get("bf16_tflops_sustained")}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -310,8 +339,10 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": workload_name(args.workload), "points_per_gpu": n_col, "boundary_points_per_group_per_gpu": n_bnd,
                        "points_per_step_job": n_pts_job, "parallelism": f"dp{world} over collocation points, 1 NCCL all-reduce of the flat gradient",
                        "optimizer": "torch.optim.Adam lr=1e-3",
-                       "l2": "per-step working set (activation stash %.1f GB + %.0f MB partial gradients) is far larger than the 126 MB L2"
-                             % (runner.plan(n_pts_rank).stash_bytes / 1e9, runner.plan(n_pts_rank).workspace_bytes / 1e6)},
+                       "paths": {"forward": "tcgen05 3xTF32" if paths & 1 else "FFMA2", "backward": "tcgen05 3xTF32 (sweep + dW GEMM)" if paths & 2 else "FFMA2",
+                                 "recompute": recompute},
+                       "l2": "per-step working set (activation stash %.1f GB, workspace %.1f GB) is far larger than the 126 MB L2"
+                             % (plan.stash_bytes / 1e9, plan.workspace_bytes / 1e9)},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / args.steps},

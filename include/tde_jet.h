@@ -167,6 +167,10 @@ int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 long long tde_launch_count(void);
 int tde_profile_begin(void);
 int tde_profile_end(double* forward_ms_total, int32_t* n_forward, double* backward_ms_total, int32_t* n_backward);
+/* after tde_profile_end: per-kernel totals. kind 0 forward, 1 reverse sweep, 2 weight-gradient GEMM (tensor-core path). */
+int tde_profile_kind(int kind, double* ms_total, int32_t* n_launches);
+/* which kernels a (net, spec, n_points) call uses: bit0 tcgen05 forward, bit1 tcgen05 reverse sweep + dW GEMM. */
+int tde_plan_paths(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points);
 
 /* Measures the sustained scalar-FFMA rate of this GPU (TFLOP/s); the FFMA kernels' roofline denominator. */
 int tde_fp32_peak_probe(double* tflops, void* stream);

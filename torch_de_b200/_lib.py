@@ -48,7 +48,7 @@ class TdeLossProgram(C.Structure):
 
 EXPORTS = ["tde_last_error", "tde_version", "tde_abi_struct_bytes", "tde_plan", "tde_jet_forward", "tde_jet_backward",
            "tde_residual_loss", "tde_adam_step", "tde_fp32_peak_probe", "tde_launch_count", "tde_profile_begin",
-           "tde_profile_end"]
+           "tde_profile_end", "tde_profile_kind", "tde_plan_paths"]
 
 _LIB = None
 
@@ -68,6 +68,8 @@ def _declare(lib):
     lib.tde_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
+    lib.tde_profile_kind.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+    lib.tde_plan_paths.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), i64]
     lib.tde_launch_count.restype = C.c_longlong
     lib.tde_launch_count.argtypes = []
     return lib

@@ -34,6 +34,7 @@ struct TcBwdParams {
     int tiles_per_bw_tile;
     float* gpart;               // per-CTA slabs
     int64_t gp_stride, gp_off_b_in, gp_off_b_hidden, gp_off_w_out, gp_off_b_out;
+    long long* dbg_buf;         // optional cycle stamps
 };
 
 __device__ __forceinline__ void slab_add(float* dst, float v, bool first) {
@@ -44,7 +45,7 @@ __device__ __forceinline__ void slab_add(float* dst, float v, bool first) {
     }
 }
 
-template <int NF, int SMASK>
+template <int NF, int SMASK, int W>
 __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __grid_constant__ TcBwdParams p) {
     using S = JetSpecT<NF, SMASK>;
     constexpr int J = S::J;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
     extern __shared__ __align__(1024) unsigned char smem_tc[];
     unsigned char* const smem_raw = smem_tc;
 
-    const int W = p.W, MB = p.MB;
+    constexpr int MB = W / 128;
     const int n_stages = p.n_stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
@@ -204,106 +205,149 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                     row0 = ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N) * W + n;
                 }
 
-                float g[N];   // Zbar of the current layer (then reused)
-                float dwo[TDE_MAX_OUT];
+                // Epilogue as 2 x (2 steps of 4 points): 8 points are unrolled so every shared/global offset is an immediate (a
+                // 16-point unroll is >200 KB of code and instruction-cache bound).  The stash values and the TMEM accumulators
+                // of the NEXT 4-point step are requested before the current step is processed.
+                constexpr int GC = kTcGroup * J;
+                float wo[TDE_MAX_OUT];
 #pragma unroll
-                for (int o = 0; o < TDE_MAX_OUT; ++o) dwo[o] = 0.0f;
-                {
-                    float wo[TDE_MAX_OUT];
+                for (int o = 0; o < TDE_MAX_OUT; ++o) wo[o] = o < p.n_out ? wout_s[o * W + n] : 0.0f;
+                uint32_t xorv[8];
 #pragma unroll
-                    for (int o = 0; o < TDE_MAX_OUT; ++o) wo[o] = o < p.n_out ? wout_s[o * W + n] : 0.0f;
-#pragma unroll
-                    for (int pt = 0; pt < kTcPoints; ++pt)
-#pragma unroll
-                        for (int c = 0; c < J; ++c) {
-                            float a = 0.0f;
-#pragma unroll
-                            for (int o = 0; o < TDE_MAX_OUT; ++o)
-                                if (o < p.n_out) a = fmaf(wo[o], seeds_s[(c * p.n_out + o) * kTcPoints + pt], a);
-                            g[pt * J + c] = a;
-                        }
-                }
+                for (int j = 0; j < 8; ++j) xorv[j] = zrow + ((kchunk ^ (uint32_t)j) << 4);
 
                 for (int l = p.L - 1; l >= 0; --l) {
-                    if (l < p.L - 1) {
-                        mbar_wait(acc_ready, acc_ph);
-                        acc_ph ^= 1;
-                        tc_fence_after();
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
-#pragma unroll
-                        for (int c0 = 0; c0 < N; c0 += 16) tmem_ld16(taddr + c0, g + c0);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        for (int a = 1; a < p.n_acc; ++a) {
-#pragma unroll
-                            for (int c0 = 0; c0 < N; c0 += 16) {
-                                float part[16];
-                                tmem_ld16(taddr + (uint32_t)(a * MB * N) + c0, part);
-                                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) g[c0 + i] += part[i];
-                            }
-                        }
-                    }
+                    const bool last = l == p.L - 1;
                     const float* srow = p.stash + (size_t)l * p.stash_layer_stride + row0;
                     float* hrow = p.hbar + (size_t)l * p.stash_layer_stride + row0;
                     float* zrow_g = p.zst + (size_t)l * p.stash_layer_stride + row0;
-                    const bool last = l == p.L - 1;
+                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && n == 0 && tile == 0 && l == 3;
+                    if (stamp) p.dbg_buf[0] = clock64();
+                    float st_next[GC];
+#pragma unroll
+                    for (int i = 0; i < GC; ++i) st_next[i] = real ? __ldcs(srow + (size_t)i * W) : 0.0f;
+                    uint32_t taddr = 0;
+                    float cur[3][GC];
+                    if (!last) {
+                        mbar_wait(acc_ready, acc_ph);
+                        acc_ph ^= 1;
+                        tc_fence_after();
+                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+                            if (a < p.n_acc) tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N), cur[a]);
+                    }
+                    if (stamp) p.dbg_buf[1] = clock64();
                     float db = 0.0f;
-                    float dw_in[TDE_MAX_IN];
+                    float dwo[TDE_MAX_OUT], dw_in[TDE_MAX_IN];
+#pragma unroll
+                    for (int o = 0; o < TDE_MAX_OUT; ++o) dwo[o] = 0.0f;
 #pragma unroll
                     for (int i = 0; i < TDE_MAX_IN; ++i) dw_in[i] = 0.0f;
+                    if (stamp) p.dbg_buf[2] = clock64();
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        unsigned char* zhi_h = zhi + (uint32_t)half * (uint32_t)(J * 1024);
+                        unsigned char* zlo_h = zlo + (uint32_t)half * (uint32_t)(J * 1024);
+                        const float* srow_h = srow + (size_t)half * (8 * J) * W;
+                        float* hrow_h = hrow + (size_t)half * (8 * J) * W;
+                        float* zrow_h = zrow_g + (size_t)half * (8 * J) * W;
+                        const float* xs_h = xs + half * 8 * p.d_in;
+                        const float* seeds_h = seeds_s + half * 8;
 #pragma unroll
-                    for (int pt = 0; pt < kTcPoints; ++pt) {
-                        float st[J], zb[J], hb[J], z[J];
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            float stg[GC], zbg[GC];
 #pragma unroll
-                        for (int c = 0; c < J; ++c) {
-                            st[c] = real ? __ldcs(srow + (size_t)(pt * J + c) * W) : 0.0f;
-                            zb[c] = g[pt * J + c];
-                        }
-                        act_backward<S, true>(p.act, st, zb, hb, z);
-                        db += hb[0];
-                        if (last) {
+                            for (int i = 0; i < GC; ++i) stg[i] = st_next[i];
+                            if (g2 == 0) {
 #pragma unroll
-                            for (int c = 0; c < J; ++c)
+                                for (int i = 0; i < GC; ++i) st_next[i] = real ? __ldcs(srow_h + (size_t)(GC + i) * W) : 0.0f;
+                            } else if (half == 0) {
 #pragma unroll
-                                for (int o = 0; o < TDE_MAX_OUT; ++o)
-                                    if (o < p.n_out) dwo[o] = fmaf(seeds_s[(c * p.n_out + o) * kTcPoints + pt], z[c], dwo[o]);
-                        }
-                        if (l >= 1) {
-#pragma unroll
-                            for (int c = 0; c < J; ++c) {
-                                const int col = pt * J + c;
-                                if (real) __stcs(hrow + (size_t)col * W, hb[c]);
-                                const uint32_t off = zrow + (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u +
-                                                     ((kchunk ^ (uint32_t)(col & 7)) << 4);
-                                float hi, lo;
-                                split_tf32(hb[c], hi, lo);
-                                *reinterpret_cast<float*>(zhi + off) = hi;
-                                *reinterpret_cast<float*>(zlo + off) = lo;
+                                for (int i = 0; i < GC; ++i) st_next[i] = real ? __ldcs(srow_h + (size_t)(2 * GC + i) * W) : 0.0f;
                             }
-                        } else {
-                            // input layer: h = W0 x + b0, h_a = W0[:, first_in[a]]
-                            const float h0 = hb[0];
+                            if (!last) {
+                                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                            for (int i = 0; i < TDE_MAX_IN; ++i)
-                                if (i < p.d_in) dw_in[i] = fmaf(h0, xs[pt * p.d_in + i], dw_in[i]);
+                                for (int i = 0; i < GC; ++i) {
+                                    float v = cur[0][i];
+                                    if (p.n_acc > 1) v += cur[1][i];
+                                    if (p.n_acc > 2) v += cur[2][i];
+                                    zbg[i] = v;
+                                }
+                                if (half * 2 + g2 + 1 < kTcPoints / kTcGroup) {
 #pragma unroll
-                            for (int a = 0; a < NF; ++a) {
-#pragma unroll
-                                for (int i = 0; i < TDE_MAX_IN; ++i)
-                                    if (i == p.first_in[a]) dw_in[i] += hb[1 + a];
+                                    for (int a = 0; a < 3; ++a)
+                                        if (a < p.n_acc)
+                                            tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + (half * 2 + g2 + 1) * GC), cur[a]);
+                                }
                             }
-                        }
-                        if (l <= p.L - 2 && real) {
 #pragma unroll
-                            for (int c = 0; c < J; ++c) __stcs(zrow_g + (size_t)(pt * J + c) * W, z[c]);
+                            for (int q = 0; q < kTcGroup; ++q) {
+                                const int pt8 = g2 * kTcGroup + q;      // compile-time 0..7
+                                float st[J], zb[J], hb[J], z[J];
+#pragma unroll
+                                for (int c = 0; c < J; ++c) st[c] = stg[q * J + c];
+                                if (last) {
+#pragma unroll
+                                    for (int c = 0; c < J; ++c) {
+                                        float a = 0.0f;
+#pragma unroll
+                                        for (int o = 0; o < TDE_MAX_OUT; ++o)
+                                            if (o < p.n_out) a = fmaf(wo[o], seeds_h[(c * p.n_out + o) * kTcPoints + pt8], a);
+                                        zb[c] = a;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < J; ++c) zb[c] = zbg[q * J + c];
+                                }
+                                act_backward<S, true>(p.act, st, zb, hb, z);
+                                db += hb[0];
+                                if (last) {
+#pragma unroll
+                                    for (int c = 0; c < J; ++c)
+#pragma unroll
+                                        for (int o = 0; o < TDE_MAX_OUT; ++o)
+                                            if (o < p.n_out) dwo[o] = fmaf(seeds_h[(c * p.n_out + o) * kTcPoints + pt8], z[c], dwo[o]);
+                                }
+                                if (l >= 1) {
+#pragma unroll
+                                    for (int c = 0; c < J; ++c) {
+                                        const int col8 = pt8 * J + c;
+                                        if (real) __stcs(hrow_h + (size_t)col8 * W, hb[c]);
+                                        const uint32_t off = (uint32_t)(col8 >> 3) * 1024u + (uint32_t)(col8 & 7) * 128u + xorv[col8 & 7];
+                                        float hi, lo;
+                                        split_tf32(hb[c], hi, lo);
+                                        *reinterpret_cast<float*>(zhi_h + off) = hi;
+                                        *reinterpret_cast<float*>(zlo_h + off) = lo;
+                                    }
+                                } else {
+                                    // input layer: h = W0 x + b0, h_a = W0[:, first_in[a]]
+                                    const float h0 = hb[0];
+#pragma unroll
+                                    for (int i = 0; i < TDE_MAX_IN; ++i)
+                                        if (i < p.d_in) dw_in[i] = fmaf(h0, xs_h[pt8 * p.d_in + i], dw_in[i]);
+#pragma unroll
+                                    for (int a = 0; a < NF; ++a) {
+#pragma unroll
+                                        for (int i = 0; i < TDE_MAX_IN; ++i)
+                                            if (i == p.first_in[a]) dw_in[i] += hb[1 + a];
+                                    }
+                                }
+                                if (l <= p.L - 2 && real) {
+#pragma unroll
+                                    for (int c = 0; c < J; ++c) __stcs(zrow_h + (size_t)(pt8 * J + c) * W, z[c]);
+                                }
+                            }
                         }
                     }
+                    if (stamp) p.dbg_buf[3] = clock64();
                     if (l >= 1) {
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(act_ready);
+                        if (stamp) p.dbg_buf[4] = clock64();
                         slab_add(gp + p.gp_off_b_hidden + (size_t)(l - 1) * W + n, db, first);
                     } else {
                         slab_add(gp + p.gp_off_b_in + n, db, first);

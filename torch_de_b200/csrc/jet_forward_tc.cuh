@@ -106,7 +106,76 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int NF, int SMASK>
+// LDW consecutive TMEM columns of this thread's lane -> registers (no wait: pair with tcgen05.wait::ld)
+template <int LDW>
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[LDW]) {
+    uint32_t r[LDW];
+    if constexpr (LDW == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+    }
+#pragma unroll
+    for (int i = 0; i < LDW; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int NC>
+__device__ __forceinline__ void tmem_ld_piece(uint32_t taddr, float* v) {
+    uint32_t r[NC];
+    if constexpr (NC == 16) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+    } else if constexpr (NC == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr));
+    } else if constexpr (NC == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(taddr));
+    } else if constexpr (NC == 2) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r[i]);
+}
+// NC consecutive columns, NC a multiple of 4 (<= 40): split into power-of-two tcgen05.ld shapes.  No wait.
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
+    if constexpr (NC >= 32) {
+        tmem_ld_piece<16>(taddr, v);
+        tmem_ld_piece<16>(taddr + 16, v + 16);
+        if constexpr (NC > 32) tmem_ld_cols<NC - 32>(taddr + 32, v + 32);
+    } else if constexpr (NC >= 16) {
+        tmem_ld_piece<16>(taddr, v);
+        if constexpr (NC > 16) tmem_ld_cols<NC - 16>(taddr + 16, v + 16);
+    } else if constexpr (NC >= 8) {
+        tmem_ld_piece<8>(taddr, v);
+        if constexpr (NC > 8) tmem_ld_cols<NC - 8>(taddr + 8, v + 8);
+    } else if constexpr (NC >= 4) {
+        tmem_ld_piece<4>(taddr, v);
+        if constexpr (NC > 4) tmem_ld_cols<NC - 4>(taddr + 4, v + 4);
+    } else if constexpr (NC >= 2) {
+        tmem_ld_piece<2>(taddr, v);
+        if constexpr (NC > 2) tmem_ld_cols<NC - 2>(taddr + 2, v + 2);
+    } else if constexpr (NC == 1) {
+        tmem_ld_piece<1>(taddr, v);
+    }
+}
+constexpr int kTcGroup = 4;        // points handled per unrolled epilogue step (16 points = 4 steps)
+
+template <int NF, int SMASK, int W>
 __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __grid_constant__ TcParams p) {
     using S = JetSpecT<NF, SMASK>;
     constexpr int J = S::J;
@@ -117,7 +186,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     extern __shared__ __align__(1024) unsigned char smem_tc[];
     unsigned char* const smem_raw = smem_tc;
 
-    const int W = p.W, MB = p.MB;
+    constexpr int MB = W / 128;
     const int n_stages = p.n_stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
@@ -276,87 +345,99 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                     stash_row = p.stash + ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N) * W + n;
                 }
 
+                // Per layer the epilogue walks the 16 points as 2 x (2 steps of 4 points): 8 points are unrolled so every
+                // shared/global offset is an immediate (a 16-point unroll is >80 KB of code and instruction-cache bound),
+                // and the TMEM columns of the next 4-point step are requested before the current step is used.
+                constexpr int GC = kTcGroup * J;          // jet columns per 4-point step
+                uint32_t xorv[8];                         // swizzled 16 B chunk offset for each (column & 7)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xorv[j] = zrow + ((kchunk ^ (uint32_t)j) << 4);
                 for (int l = 0; l < p.L; ++l) {
-                    float hbuf[N];
+                    float* srow = stash_row ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
+                    float wrow[TDE_MAX_IN], wf[NF > 0 ? NF : 1];
+                    float bn;
+                    uint32_t taddr = 0;
+                    float cur[3][GC];
                     if (l == 0) {
-                        float wrow[TDE_MAX_IN];
 #pragma unroll
                         for (int i = 0; i < TDE_MAX_IN; ++i) wrow[i] = i < p.d_in ? __ldg(p.w_in + n * p.d_in + i) : 0.0f;
-                        const float bn = __ldg(p.b_in + n);
-                        float wf[NF > 0 ? NF : 1];
+                        bn = __ldg(p.b_in + n);
 #pragma unroll
                         for (int a = 0; a < NF; ++a) wf[a] = __ldg(p.w_in + n * p.d_in + p.first_in[a]);
-#pragma unroll
-                        for (int pt = 0; pt < kTcPoints; ++pt) {
-                            float h0 = bn;
-#pragma unroll
-                            for (int i = 0; i < TDE_MAX_IN; ++i)
-                                if (i < p.d_in) h0 = fmaf(wrow[i], xs[pt * p.d_in + i], h0);
-                            hbuf[pt * J] = h0;
-#pragma unroll
-                            for (int a = 0; a < NF; ++a) hbuf[pt * J + 1 + a] = wf[a];
-#pragma unroll
-                            for (int q = 0; q < S::NS; ++q) hbuf[pt * J + 1 + NF + q] = 0.0f;
-                        }
                     } else {
-                        const bool stamp = p.dbg_buf && blockIdx.x == 0 && n == 0 && tile == 0 && l == 2;
-                        if (stamp) p.dbg_buf[0] = clock64();
+                        bn = __ldg(p.b_hidden + (size_t)(l - 1) * W + n);
                         mbar_wait(acc_ready, acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
-                        if (stamp) p.dbg_buf[1] = clock64();
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
+                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
 #pragma unroll
-                        for (int c0 = 0; c0 < N; c0 += 16) tmem_ld16(taddr + c0, hbuf + c0);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        for (int a = 1; a < p.n_acc; ++a) {
+                        for (int a = 0; a < 3; ++a)
+                            if (a < p.n_acc) tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N), cur[a]);
+                    }
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        unsigned char* zhi_h = zhi + (uint32_t)half * (uint32_t)(J * 1024);   // 8 points = J column groups of 8
+                        unsigned char* zlo_h = zlo + (uint32_t)half * (uint32_t)(J * 1024);
+                        float* srow_h = srow ? srow + (size_t)half * (8 * J) * W : nullptr;
+                        const float* xs_h = xs + half * 8 * p.d_in;
 #pragma unroll
-                            for (int c0 = 0; c0 < N; c0 += 16) {
-                                float part[16];
-                                tmem_ld16(taddr + (uint32_t)(a * MB * N) + c0, part);
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            float hg[GC];
+                            if (l != 0) {
                                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) hbuf[c0 + i] += part[i];
+                                for (int i = 0; i < GC; ++i) {
+                                    float v = cur[0][i];
+                                    if (p.n_acc > 1) v += cur[1][i];
+                                    if (p.n_acc > 2) v += cur[2][i];
+                                    hg[i] = v;
+                                }
+                                if (half * 2 + g2 + 1 < kTcPoints / kTcGroup) {
+#pragma unroll
+                                    for (int a = 0; a < 3; ++a)
+                                        if (a < p.n_acc)
+                                            tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + (half * 2 + g2 + 1) * GC), cur[a]);
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < kTcGroup; ++q) {
+                                const int pt8 = g2 * kTcGroup + q;          // compile-time 0..7
+                                float h[J], z[J];
+                                if (l == 0) {
+                                    float h0 = bn;
+#pragma unroll
+                                    for (int i = 0; i < TDE_MAX_IN; ++i)
+                                        if (i < p.d_in) h0 = fmaf(wrow[i], xs_h[pt8 * p.d_in + i], h0);
+                                    h[0] = h0;
+#pragma unroll
+                                    for (int a = 0; a < NF; ++a) h[1 + a] = wf[a];
+#pragma unroll
+                                    for (int qq = 0; qq < S::NS; ++qq) h[1 + NF + qq] = 0.0f;
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < J; ++c) h[c] = hg[q * J + c];
+                                    h[0] += bn;
+                                }
+                                act_forward<S>(p.act, h, z);      // h[0] now holds the value to stash (t | h0)
+#pragma unroll
+                                for (int c = 0; c < J; ++c) {
+                                    const int col8 = pt8 * J + c;           // column within this half (compile-time)
+                                    if (srow_h) __stcs(srow_h + (size_t)col8 * W, h[c]);      // one 128 B line per warp store
+                                    const uint32_t off = (uint32_t)(col8 >> 3) * 1024u + (uint32_t)(col8 & 7) * 128u + xorv[col8 & 7];
+                                    float hi, lo;
+                                    split_tf32(z[c], hi, lo);
+                                    *reinterpret_cast<float*>(zhi_h + off) = hi;
+                                    *reinterpret_cast<float*>(zlo_h + off) = lo;
+                                }
                             }
                         }
-                        const float bn = __ldg(p.b_hidden + (size_t)(l - 1) * W + n);
-#pragma unroll
-                        for (int pt = 0; pt < kTcPoints; ++pt) hbuf[pt * J] += bn;
-                        if (stamp) p.dbg_buf[2] = clock64();
                     }
-                    // jet activation, stash, split and store the next B operand
-                    float* srow = stash_row ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
-#pragma unroll
-                    for (int pt = 0; pt < kTcPoints; ++pt) {
-                        float h[J], z[J];
-#pragma unroll
-                        for (int c = 0; c < J; ++c) h[c] = hbuf[pt * J + c];
-                        act_forward<S>(p.act, h, z);
-#pragma unroll
-                        for (int c = 0; c < J; ++c) {
-                            hbuf[pt * J + c] = h[c];     // (t | h_c) for the stash
-                            const int col = pt * J + c;
-                            const uint32_t off = zrow + (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u + ((kchunk ^ (uint32_t)(col & 7)) << 4);
-                            float hi, lo;
-                            split_tf32(z[c], hi, lo);
-                            *reinterpret_cast<float*>(zhi + off) = hi;
-                            *reinterpret_cast<float*>(zlo + off) = lo;
-                        }
-                    }
-                    const bool stamp2 = p.dbg_buf && blockIdx.x == 0 && n == 0 && tile == 0 && l == 2;
-                    if (stamp2) p.dbg_buf[3] = clock64();
-                    if (srow) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) __stcs(srow + (size_t)i * W, hbuf[i]);   // one 128 B line per warp store
-                    }
-                    if (stamp2) p.dbg_buf[4] = clock64();
                     if (l < p.L - 1) {
                         // publish: smem writes -> async proxy, TMEM reads retired, then one arrive per warp
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(act_ready);
-                        if (stamp2) p.dbg_buf[5] = clock64();
                     }
                 }
                 epi_sync();   // every neuron's last-layer z is in the planes

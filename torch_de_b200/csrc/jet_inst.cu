@@ -27,7 +27,7 @@ cudaError_t TDE_CAT(launch_backward_, TDE_NF, _, TDE_SMASK)(const JetParams& p, 
 }
 
 cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p, int grid, int smem, cudaStream_t st) {
-    auto k = jet_forward_tc_kernel<TDE_NF, TDE_SMASK>;
+    auto k = p.W == 256 ? jet_forward_tc_kernel<TDE_NF, TDE_SMASK, 256> : jet_forward_tc_kernel<TDE_NF, TDE_SMASK, 128>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
@@ -46,7 +46,7 @@ cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p,
 }
 
 cudaError_t TDE_CAT(launch_backward_tc_, TDE_NF, _, TDE_SMASK)(const TcBwdParams& p, int grid, int smem, cudaStream_t st) {
-    auto k = jet_backward_tc_kernel<TDE_NF, TDE_SMASK>;
+    auto k = p.W == 256 ? jet_backward_tc_kernel<TDE_NF, TDE_SMASK, 256> : jet_backward_tc_kernel<TDE_NF, TDE_SMASK, 128>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};

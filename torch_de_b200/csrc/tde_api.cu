@@ -37,7 +37,7 @@ long long g_launches = 0;
 bool g_profiling = false;
 struct TimedLaunch {
     cudaEvent_t e0, e1;
-    int kind;  // 0 forward, 1 backward
+    int kind;  // 0 forward, 1 reverse sweep, 2 weight-gradient GEMM (tensor-core path only)
 };
 std::vector<TimedLaunch> g_timed;
 
@@ -652,6 +652,12 @@ int tde_plan(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points, TdePla
     return 0;
 }
 
+int tde_plan_paths(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points) {
+    Geometry g;
+    if (make_geometry(net, spec, n_points, &g)) return -1;
+    return (g.use_tc ? 1 : 0) | (g.use_tc_bwd ? 2 : 0);
+}
+
 int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points, float* out,
                     int64_t ld_out, float* stash, void* workspace, void* stream) {
     Geometry g;
@@ -732,9 +738,25 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         d.n_tiles = g.tc_tiles; d.L = g.L; d.W = g.W; d.MB = g.tc_mb; d.J = g.J;
         d.hbar = t.hbar; d.zst = t.zst; d.stash_layer_stride = t.stash_layer_stride; d.tiles_per_bw_tile = t.tiles_per_bw_tile;
         d.gpart = t.gpart; d.gp_stride = g.gp_stride; d.gp_off_hidden = g.g_hidden;
+        static long long* bdbg = nullptr;
+        const char* dbg_env = getenv("TDE_TC_DBG");
+        if (dbg_env && (atoi(dbg_env) & 4)) {
+            if (!bdbg) { cudaMalloc(&bdbg, 16 * sizeof(long long)); cudaMemset(bdbg, 0, 16 * sizeof(long long)); }
+            t.dbg_buf = bdbg;
+        }
         {
             ScopedTimer timer(st, 1);
             TDE_CUDA(g.disp->bwd_tc(t, (int)g.grid_b1, g.tc_smem, st));
+        }
+        if (t.dbg_buf) {
+            long long h[16];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, bdbg, sizeof h, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[tc bwd dbg] stash_ld_issue+wait_acc %lld  tmem_ld %lld  adjoint+stores %lld  publish %lld\n", h[1] - h[0],
+                    h[2] - h[1], h[3] - h[2], h[4] - h[3]);
+        }
+        {
+            ScopedTimer timer(st, 2);
             if (g.L >= 2) {
                 auto k = tde::jet_dw_tc_kernel<0>;
                 TDE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g.dw_smem));
@@ -817,10 +839,20 @@ int tde_profile_begin(void) {
     return 0;
 }
 
+static double g_prof_ms[3] = {0.0, 0.0, 0.0};
+static int g_prof_cnt[3] = {0, 0, 0};
+
+int tde_profile_kind(int kind, double* ms_total, int32_t* n) {
+    if (kind < 0 || kind > 2) return fail("profile kind %d out of range (0 forward, 1 reverse sweep, 2 weight-gradient GEMM)", kind);
+    if (ms_total) *ms_total = g_prof_ms[kind];
+    if (n) *n = g_prof_cnt[kind];
+    return 0;
+}
+
 int tde_profile_end(double* fwd_ms, int32_t* n_fwd, double* bwd_ms, int32_t* n_bwd) {
     g_profiling = false;
-    double ms[2] = {0.0, 0.0};
-    int cnt[2] = {0, 0};
+    double ms[3] = {0.0, 0.0, 0.0};
+    int cnt[3] = {0, 0, 0};
     for (auto& t : g_timed) {
         TDE_CUDA(cudaEventSynchronize(t.e1));
         float m = 0.f;
@@ -831,9 +863,13 @@ int tde_profile_end(double* fwd_ms, int32_t* n_fwd, double* bwd_ms, int32_t* n_b
         cudaEventDestroy(t.e1);
     }
     g_timed.clear();
+    for (int k = 0; k < 3; ++k) {
+        g_prof_ms[k] = ms[k];
+        g_prof_cnt[k] = cnt[k];
+    }
     if (fwd_ms) *fwd_ms = ms[0];
     if (n_fwd) *n_fwd = cnt[0];
-    if (bwd_ms) *bwd_ms = ms[1];
+    if (bwd_ms) *bwd_ms = ms[1] + ms[2];     // whole reverse pass (sweep + weight-gradient GEMM when it is a separate kernel)
     if (n_bwd) *n_bwd = cnt[1];
     return 0;
 }
