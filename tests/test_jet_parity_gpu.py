@@ -243,3 +243,87 @@ def test_recompute_mode_matches_stash_mode(monkeypatch):
         (out['u_xx'] * out['v_y'] + out['p_x'].pow(2)).mean().backward()
         grads[frac] = torch.cat([p.grad.flatten().cpu() for lin in lins for p in (lin.weight, lin.bias)])
     assert rel_l2(grads[1e-9], grads[0.55]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, 3xTF32) path: every shape class it accepts, against the oracle in float64
+# ---------------------------------------------------------------------------------------------------------------------
+def _oracle_case(d_in, n_out, width, n_act, ins, outs, ders, act, n_pts, seed):
+    from oracle import ref_autograd as O
+    params = O.init_mlp_params(d_in, n_out, width, n_act, seed=seed)
+    net = T.MLP(d_in, n_out, width, n_act - 1, activation=act)
+    lins, _ = T.extract_layers(net)
+    with torch.no_grad():
+        for i, lin in enumerate(lins):
+            lin.weight.copy_(params[2 * i]); lin.bias.copy_(params[2 * i + 1])
+    net = net.cuda()
+    x = torch.rand(n_pts, d_in, generator=torch.Generator().manual_seed(seed + 1)) * 2 - 1
+    imap = O.derivative_index_map(ins, outs, ders)
+    pinn = T.DE_Getter(net, ins, outs, ders)
+    out = pinn(x.cuda())['all']
+    pr = [p.double().requires_grad_(True) for p in params]
+    ref = O.streams(pr, x.double(), imap, act)
+    weights = {k: 0.3 + 0.1 * i for i, k in enumerate(imap)}
+    loss = sum(weights[k] * out[k].pow(2).mean() for k in imap)
+    loss.backward()
+    gref = torch.autograd.grad(sum(weights[k] * ref[k].pow(2).mean() for k in imap), pr)
+    got = torch.cat([p.grad.flatten().cpu() for lin in lins for p in (lin.weight, lin.bias)])
+    return pinn, out, ref, got, torch.cat([g.flatten() for g in gref])
+
+
+@pytest.mark.parametrize('case', [
+    dict(d_in=2, n_out=1, width=256, n_act=4, ins=['x', 't'], outs=['u'], ders=['u_x', 'u_t', 'u_xx'], act='tanh'),          # J=4
+    dict(d_in=3, n_out=3, width=128, n_act=3, ins=['x', 'y', 't'], outs=['u', 'v', 'p'], ders=['u_t', 'u_xx', 'v_yy', 'p_x'], act='tanh'),   # J=6, 2 accumulator sets
+    dict(d_in=1, n_out=1, width=256, n_act=3, ins=['t'], outs=['u'], ders=['u_t', 'u_tt'], act='sin'),                      # J=3, sin
+    dict(d_in=2, n_out=2, width=128, n_act=5, ins=['x', 'y'], outs=['u', 'v'], ders=[], act='tanh'),                        # J=1 (value only)
+    dict(d_in=2, n_out=1, width=200, n_act=3, ins=['x', 't'], outs=['u'], ders=['u_xt'], act='tanh'),                       # padded width, mixed -> J=6
+    dict(d_in=2, n_out=3, width=256, n_act=3, ins=['x', 'y'], outs=['u', 'v', 'p'], ders=['u_xx', 'v_yy', 'p_x'], act='tanh'),
+])
+@pytest.mark.parametrize('n_pts', [1, 17, 333])
+def test_tensor_core_path_shapes(case, n_pts):
+    pinn, out, ref, got, gref = _oracle_case(n_pts=n_pts, seed=21, **case)
+    runner = pinn.deriv_method._full
+    import ctypes as C
+    from torch_de_b200 import _lib
+    paths = _lib.lib().tde_plan_paths(C.byref(runner._net), C.byref(runner._spec), n_pts)
+    assert paths == 3, f'expected the tcgen05 forward+backward path, got {paths}'
+    for k in ref:
+        assert rel_l2(out[k].detach().cpu(), ref[k].detach()) < TOL_STREAM, k
+        assert max_rel(out[k].detach().cpu(), ref[k].detach()) < TOL_STREAM, k
+    assert rel_l2(got, gref) < TOL_LOSS
+    assert max_rel(got, gref) < TOL_LOSS
+
+
+def test_tensor_core_and_ffma_paths_agree(monkeypatch):
+    z, owl, params, groups = load('ldc')
+    res = {}
+    for no_tc in ('1', '0'):
+        monkeypatch.setenv('TDE_NO_TC', no_tc)
+        res[no_tc] = run_product('ldc')
+    for k in res['0'][4].derivatives:
+        assert rel_l2(res['0'][5]['all'][k].detach().cpu(), res['1'][5]['all'][k].detach().cpu()) < TOL_STREAM
+    g0 = torch.cat([g.flatten() for g in res['0'][8]])
+    g1 = torch.cat([g.flatten() for g in res['1'][8]])
+    assert rel_l2(g0, g1) < 1e-5
+
+
+def test_tensor_core_recompute_mode(monkeypatch):
+    from torch_de_b200 import engine as E
+    grads = {}
+    for frac in (0.7, 1e-9):
+        monkeypatch.setattr(E, 'STASH_FRACTION_OF_FREE', frac)
+        torch.manual_seed(3)
+        net = T.MLP(2, 1, 128, 3).cuda()
+        pinn = T.DE_Getter(net, ['x', 't'], ['u'], ['u_x', 'u_xx'])
+        x = torch.rand(3000, 2, generator=torch.Generator().manual_seed(1)).cuda()
+        out = pinn(x)['all']
+        (out['u_xx'] * out['u_x'] + out['u'].pow(2)).mean().backward()
+        grads[frac] = torch.cat([p.grad.flatten().cpu() for p in net.parameters()])
+    assert rel_l2(grads[1e-9], grads[0.7]) < 1e-5
+
+
+def test_tensor_core_gradients_bitwise_repeatable():
+    a = run_product('ldc')[-1]
+    b = run_product('ldc')[-1]
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
