@@ -502,43 +502,64 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                 const float* zsrc = p.zst + (size_t)(l - 1) * p.stash_layer_stride;
                 for (int64_t t0 = 0; t0 < my_tiles; t0 += kDwFlushTiles) {
                     const int64_t t1 = t0 + kDwFlushTiles < my_tiles ? t0 + kDwFlushTiles : my_tiles;
-                    for (int64_t t = t0; t < t1; ++t) {
-                        const int64_t tile = blockIdx.x + t * gridDim.x;
+                    // Loads run 3 stages ahead of the stores (ring of 4 register buffers): ~48 KB in flight per SM covers the
+                    // HBM latency at the rate the MMAs consume stages.
+                    const int total = (int)(t1 - t0) * n_ks;
+                    int64_t lt = t0;       // load cursor: tile, k-step
+                    int lks = 0;
+                    float hv[4][8], zv[4][8];
+                    auto issue_loads = [&](float (&h8)[8], float (&z8)[8]) {
+                        const int64_t tile = blockIdx.x + lt * gridDim.x;
                         const int64_t bw_tile = tile / p.tiles_per_bw_tile;
                         const int sub = (int)(tile - bw_tile * p.tiles_per_bw_tile);
-                        const size_t row0 = ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N) * W + n;
-                        for (int ks = 0; ks < n_ks; ++ks) {
-                            float hv[8], zv[8];
+                        const size_t row0 = ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N + (size_t)lks * 8) * W + n;
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                hv[c] = __ldcs(hsrc + row0 + (size_t)(ks * 8 + c) * W);
-                                zv[c] = __ldcs(zsrc + row0 + (size_t)(ks * 8 + c) * W);
-                            }
-                            mbar_wait(&empty[s], ph ^ 1);
-                            unsigned char* st = stages + (size_t)s * stage_bytes;
+                        for (int c = 0; c < 8; ++c) {
+                            h8[c] = __ldcs(hsrc + row0 + (size_t)c * W);
+                            z8[c] = __ldcs(zsrc + row0 + (size_t)c * W);
+                        }
+                        if (++lks == n_ks) {
+                            lks = 0;
+                            ++lt;
+                        }
+                    };
+                    auto store_stage = [&](const float (&h8)[8], const float (&z8)[8]) {
+                        mbar_wait(&empty[s], ph ^ 1);
+                        unsigned char* st = stages + (size_t)s * stage_bytes;
 #pragma unroll
-                            for (int kg = 0; kg < 2; ++kg) {
-                                float4 hh, hl, zh, zl;
-                                split_tf32(hv[4 * kg + 0], hh.x, hl.x);
-                                split_tf32(hv[4 * kg + 1], hh.y, hl.y);
-                                split_tf32(hv[4 * kg + 2], hh.z, hl.z);
-                                split_tf32(hv[4 * kg + 3], hh.w, hl.w);
-                                split_tf32(zv[4 * kg + 0], zh.x, zl.x);
-                                split_tf32(zv[4 * kg + 1], zh.y, zl.y);
-                                split_tf32(zv[4 * kg + 2], zh.z, zl.z);
-                                split_tf32(zv[4 * kg + 3], zh.w, zl.w);
-                                const uint32_t o = (uint32_t)kg * lbo + rowoff;
-                                *reinterpret_cast<float4*>(st + o) = hh;
-                                *reinterpret_cast<float4*>(st + op_bytes + o) = hl;
-                                *reinterpret_cast<float4*>(st + 2 * op_bytes + o) = zh;
-                                *reinterpret_cast<float4*>(st + 3 * op_bytes + o) = zl;
-                            }
-                            fence_proxy_async();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&full[s]);
-                            if (++s == kDwStages) {
-                                s = 0;
-                                ph ^= 1;
+                        for (int kg = 0; kg < 2; ++kg) {
+                            float4 hh, hl, zh, zl;
+                            split_tf32(h8[4 * kg + 0], hh.x, hl.x);
+                            split_tf32(h8[4 * kg + 1], hh.y, hl.y);
+                            split_tf32(h8[4 * kg + 2], hh.z, hl.z);
+                            split_tf32(h8[4 * kg + 3], hh.w, hl.w);
+                            split_tf32(z8[4 * kg + 0], zh.x, zl.x);
+                            split_tf32(z8[4 * kg + 1], zh.y, zl.y);
+                            split_tf32(z8[4 * kg + 2], zh.z, zl.z);
+                            split_tf32(z8[4 * kg + 3], zh.w, zl.w);
+                            const uint32_t o = (uint32_t)kg * lbo + rowoff;
+                            *reinterpret_cast<float4*>(st + o) = hh;
+                            *reinterpret_cast<float4*>(st + op_bytes + o) = hl;
+                            *reinterpret_cast<float4*>(st + 2 * op_bytes + o) = zh;
+                            *reinterpret_cast<float4*>(st + 3 * op_bytes + o) = zl;
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[s]);
+                        if (++s == kDwStages) {
+                            s = 0;
+                            ph ^= 1;
+                        }
+                    };
+#pragma unroll
+                    for (int b = 0; b < 3; ++b)
+                        if (b < total) issue_loads(hv[b], zv[b]);
+                    for (int j = 0; j < total; j += 4) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            if (j + b < total) {
+                                if (j + b + 3 < total) issue_loads(hv[(b + 3) & 3], zv[(b + 3) & 3]);
+                                store_stage(hv[b], zv[b]);
                             }
                         }
                     }
