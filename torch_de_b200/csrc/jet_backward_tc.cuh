@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
 // ---------------------------------------------------------------------------------------------------------------------
 // dW_l = Hbar_l^T-contract Z_{l-1} on the tensor cores
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDwThreads = 384;       // warp 1: MMA issuer, warps 4..11: loaders / flushers (one thread per neuron)
+constexpr int kDwThreads = 640;       // warp 1: MMA issuer, warps 4..11: Hbar loaders + flushers, warps 12..19: Z loaders (one thread per neuron)
 constexpr int kDwStages = 6;          // operand stages, one 8-column k-step each
 constexpr int kDwFlushTiles = 8;      // accumulator is flushed to the slab after this many 16-point tiles
 
@@ -413,10 +413,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
     unsigned char* stages = smem_raw + 1024;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_ld_warps = 4 * MB;
+    const int n_ld_warps = 4 * MB;          // per operand
     if (tid == 0) {
         for (int s = 0; s < kDwStages; ++s) {
-            mbar_init(&full[s], n_ld_warps);
+            mbar_init(&full[s], 2 * n_ld_warps);
             mbar_init(&empty[s], 1);
         }
         mbar_init(acc_done, 1);
@@ -436,7 +436,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
     const int64_t my_tiles = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (warp == 1) {
             const bool leader = elect_one();
             // D = F32, A = B = TF32 K-major, N = W (k neurons), M = 128
@@ -483,8 +482,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
-        const int e = warp - 4;
+        const int which = (warp - 4) >> 3;        // 0: Hbar loader (+ flusher), 1: Z loader
+        const int e = (warp - 4) & 7;
         if (e < n_ld_warps) {
             const int quarter = warp & 3;
             const int mb = e >> 2;
@@ -507,41 +506,33 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                     const int total = (int)(t1 - t0) * n_ks;
                     int64_t lt = t0;       // load cursor: tile, k-step
                     int lks = 0;
-                    float hv[4][8], zv[4][8];
-                    auto issue_loads = [&](float (&h8)[8], float (&z8)[8]) {
+                    float hv[4][8];
+                    const float* src = which ? zsrc : hsrc;
+                    auto issue_loads = [&](float (&h8)[8]) {
                         const int64_t tile = blockIdx.x + lt * gridDim.x;
                         const int64_t bw_tile = tile / p.tiles_per_bw_tile;
                         const int sub = (int)(tile - bw_tile * p.tiles_per_bw_tile);
                         const size_t row0 = ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N + (size_t)lks * 8) * W + n;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            h8[c] = __ldcs(hsrc + row0 + (size_t)c * W);
-                            z8[c] = __ldcs(zsrc + row0 + (size_t)c * W);
-                        }
+                        for (int c = 0; c < 8; ++c) h8[c] = __ldcs(src + row0 + (size_t)c * W);
                         if (++lks == n_ks) {
                             lks = 0;
                             ++lt;
                         }
                     };
-                    auto store_stage = [&](const float (&h8)[8], const float (&z8)[8]) {
+                    auto store_stage = [&](const float (&h8)[8]) {
                         mbar_wait(&empty[s], ph ^ 1);
-                        unsigned char* st = stages + (size_t)s * stage_bytes;
+                        unsigned char* st = stages + (size_t)s * stage_bytes + (size_t)which * 2 * op_bytes;   // A_hi|A_lo or B_hi|B_lo
 #pragma unroll
                         for (int kg = 0; kg < 2; ++kg) {
-                            float4 hh, hl, zh, zl;
+                            float4 hh, hl;
                             split_tf32(h8[4 * kg + 0], hh.x, hl.x);
                             split_tf32(h8[4 * kg + 1], hh.y, hl.y);
                             split_tf32(h8[4 * kg + 2], hh.z, hl.z);
                             split_tf32(h8[4 * kg + 3], hh.w, hl.w);
-                            split_tf32(z8[4 * kg + 0], zh.x, zl.x);
-                            split_tf32(z8[4 * kg + 1], zh.y, zl.y);
-                            split_tf32(z8[4 * kg + 2], zh.z, zl.z);
-                            split_tf32(z8[4 * kg + 3], zh.w, zl.w);
                             const uint32_t o = (uint32_t)kg * lbo + rowoff;
                             *reinterpret_cast<float4*>(st + o) = hh;
                             *reinterpret_cast<float4*>(st + op_bytes + o) = hl;
-                            *reinterpret_cast<float4*>(st + 2 * op_bytes + o) = zh;
-                            *reinterpret_cast<float4*>(st + 3 * op_bytes + o) = zl;
                         }
                         fence_proxy_async();
                         __syncwarp();
@@ -553,16 +544,17 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                     };
 #pragma unroll
                     for (int b = 0; b < 3; ++b)
-                        if (b < total) issue_loads(hv[b], zv[b]);
+                        if (b < total) issue_loads(hv[b]);
                     for (int j = 0; j < total; j += 4) {
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
                             if (j + b < total) {
-                                if (j + b + 3 < total) issue_loads(hv[(b + 3) & 3], zv[(b + 3) & 3]);
-                                store_stage(hv[b], zv[b]);
+                                if (j + b + 3 < total) issue_loads(hv[(b + 3) & 3]);
+                                store_stage(hv[b]);
                             }
                         }
                     }
+                    if (which) continue;      // Z loaders do not own TMEM lanes
                     // ---- flush the accumulator rows of this thread's neuron into the slab ----
                     mbar_wait(acc_done, done_ph);
                     done_ph ^= 1;
