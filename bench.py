@@ -244,6 +244,8 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
+    step()              # settle: one more untimed step after the first full synchronisation (allocator / clocks steady)
+    barrier()
 
     launches0 = lib.tde_launch_count()
     lib.tde_profile_begin()
@@ -304,9 +306,17 @@ def run_ours(args, rank, local_rank, world):
         k["launch_ms"] = k["ms"] / max(1, k["launches"])
         k["share_of_step"] = k["ms"] / ms_total
         del k["flops"], k["tensor"], k["ms"]
+    # DRAM bytes per point measured by `ncu --set full` at this workload (profiles/r01_tc_kernels_ncu_full_summary.csv:
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 510 000 points); other workloads: not captured.
+    traffic_per_point = {"jet_forward_tc_kernel": (0.010600 + 20.862975) * 1e9 / 510000,
+                         "jet_backward_tc_kernel": (20.935656 + 36.552685) * 1e9 / 510000,
+                         "jet_dw_tc_kernel": (37.014830 + 1.951827) * 1e9 / 510000} if args.workload == "ldc" else {}
+    for k in kernels:
+        per_pt = traffic_per_point.get(k["kernel"])
+        k["traffic"] = per_pt * pts_total / max(1, k["launches"]) if per_pt else None
     dom = max(kernels, key=lambda k: k["share_of_step"])
     roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s",
-                "frac": dom["frac"], "traffic": None,
+                "frac": dom["frac"], "traffic": dom["traffic"],
                 "peak_source": tensor_src if dom["bound"] == "tensor" else fp32_src,
                 "launch_ms": dom["launch_ms"], "share_of_step": dom["share_of_step"], "kernels": kernels,
                 "fp32_ffma_peak_probe": peak.value,
