@@ -12,6 +12,7 @@
 //      private gradient slab every few tiles (FP32 RED, single writer) so the tensor core's round-toward-zero accumulation
 //      never runs long enough to bias the gradient.
 #pragma once
+#include <type_traits>
 #include "jet_forward_tc.cuh"
 
 namespace tde {
@@ -216,8 +217,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
 #pragma unroll
                 for (int j = 0; j < 8; ++j) xorv[j] = zrow + ((kchunk ^ (uint32_t)j) << 4);
 
-                for (int l = p.L - 1; l >= 0; --l) {
-                    const bool last = l == p.L - 1;
+                // The body is instantiated three times (last hidden layer: adjoint seeded from the output layer; middle layers;
+                // input layer) so the hot middle-layer code carries none of the special-case registers or branches.
+                auto layer_body = [&](auto kind_c, const int l) {
+                    constexpr int KIND = decltype(kind_c)::value;     // 2 last, 1 middle, 0 input layer
+                    constexpr bool last = KIND == 2;
                     const float* srow = p.stash + (size_t)l * p.stash_layer_stride + row0;
                     float* hrow = p.hbar + (size_t)l * p.stash_layer_stride + row0;
                     float* zrow_g = p.zst + (size_t)l * p.stash_layer_stride + row0;
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                                         for (int o = 0; o < TDE_MAX_OUT; ++o)
                                             if (o < p.n_out) dwo[o] = fmaf(seeds_h[(c * p.n_out + o) * kTcPoints + pt8], z[c], dwo[o]);
                                 }
-                                if (l >= 1) {
+                                if constexpr (KIND >= 1) {
 #pragma unroll
                                     for (int c = 0; c < J; ++c) {
                                         const int col8 = pt8 * J + c;
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                                             if (i == p.first_in[a]) dw_in[i] += hb[1 + a];
                                     }
                                 }
-                                if (l <= p.L - 2 && real) {
+                                if (KIND != 2 && real) {
 #pragma unroll
                                     for (int c = 0; c < J; ++c) __stcs(zrow_h + (size_t)(pt8 * J + c) * W, z[c]);
                                 }
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                         }
                     }
                     if (stamp) p.dbg_buf[3] = clock64();
-                    if (l >= 1) {
+                    if constexpr (KIND >= 1) {
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
@@ -360,7 +364,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                         for (int o = 0; o < TDE_MAX_OUT; ++o)
                             if (o < p.n_out) slab_add(gp + p.gp_off_w_out + (size_t)o * W + n, dwo[o], first);
                     }
-                }
+                };
+                layer_body(std::integral_constant<int, 2>{}, p.L - 1);
+                for (int l = p.L - 2; l >= 1; --l) layer_body(std::integral_constant<int, 1>{}, l);
+                layer_body(std::integral_constant<int, 0>{}, 0);
                 if (et < p.n_out) {
                     float s = 0.0f;
                     for (int pt = 0; pt < kTcPoints; ++pt) s += seeds_s[(size_t)et * kTcPoints + pt];   // channel-0 rows come first

@@ -11,6 +11,7 @@
 //             every point of the tile, which is exactly what the jet activation needs (no cross-lane exchange).
 // Roles: warp 0 weight producer, warp 1 MMA issuer (one elected thread), warps 4.. epilogue (1 thread per neuron).
 #pragma once
+#include <type_traits>
 #include "jet_common.cuh"
 
 namespace tde {
@@ -352,13 +353,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                 uint32_t xorv[8];                         // swizzled 16 B chunk offset for each (column & 7)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) xorv[j] = zrow + ((kchunk ^ (uint32_t)j) << 4);
-                for (int l = 0; l < p.L; ++l) {
+                auto layer_body = [&](auto first_c, const int l) {
+                    constexpr bool kFirst = decltype(first_c)::value;     // input layer (no GEMM) vs hidden layers
                     float* srow = stash_row ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
                     float wrow[TDE_MAX_IN], wf[NF > 0 ? NF : 1];
                     float bn;
                     uint32_t taddr = 0;
                     float cur[3][GC];
-                    if (l == 0) {
+                    if constexpr (kFirst) {
 #pragma unroll
                         for (int i = 0; i < TDE_MAX_IN; ++i) wrow[i] = i < p.d_in ? __ldg(p.w_in + n * p.d_in + i) : 0.0f;
                         bn = __ldg(p.b_in + n);
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
 #pragma unroll
                         for (int g2 = 0; g2 < 2; ++g2) {
                             float hg[GC];
-                            if (l != 0) {
+                            if constexpr (!kFirst) {
                                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                                 for (int i = 0; i < GC; ++i) {
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                             for (int q = 0; q < kTcGroup; ++q) {
                                 const int pt8 = g2 * kTcGroup + q;          // compile-time 0..7
                                 float h[J], z[J];
-                                if (l == 0) {
+                                if constexpr (kFirst) {
                                     float h0 = bn;
 #pragma unroll
                                     for (int i = 0; i < TDE_MAX_IN; ++i)
@@ -439,7 +441,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                         __syncwarp();
                         if (lane == 0) mbar_arrive(act_ready);
                     }
-                }
+                };
+                layer_body(std::true_type{}, 0);
+                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, l);
                 epi_sync();   // every neuron's last-layer z is in the planes
 
                 // ---- output layer: one thread per jet column, z = hi + lo ----
