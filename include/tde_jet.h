@@ -37,6 +37,9 @@ extern "C" {
 #define TDE_ACT_NONE 0
 #define TDE_ACT_TANH 1
 #define TDE_ACT_SIN 2
+/* OR-ed into layers[0].act: the first layer is torch_DE's Fourier embedding, out = act(cat[sin(Wx+b), cos(Wx+b)]) over
+ * out_features/2 frequencies (Networks.py:53-75,104-120).  The caller passes the duplicated weight/bias (rows f and f+half equal). */
+#define TDE_ACT_FOURIER 0x100
 
 #define TDE_MAX_LAYERS 24
 #define TDE_MAX_IN 8

@@ -64,6 +64,47 @@ def mlp_apply(params: Sequence[Tensor], x: Tensor, activation: str = 'tanh') -> 
     return torch.nn.functional.linear(x, params[-2], params[-1])
 
 
+def fourier_net_apply(sd: Dict[str, Tensor], x: Tensor, activation: str, n_hidden: int, rwf: bool) -> Tensor:
+    """Fourier_Net.forward (Networks.py:104-120) from its state-dict tensors: Fourier_Embedding (:73-75) then
+    activation(Linear) layers; RWF_Linear (:49-50) multiplies v by the per-row scale s."""
+    act = getattr(torch, activation)
+
+    def lin(prefix, z):
+        if rwf:
+            return torch.nn.functional.linear(z, sd[prefix + '.v'] * sd[prefix + '.s'], sd[prefix + '.bias'])
+        return torch.nn.functional.linear(z, sd[prefix + '.weight'], sd[prefix + '.bias'])
+
+    h = torch.nn.functional.linear(x, sd['linear_in.weight'])
+    z = act(torch.cat([torch.sin(h), torch.cos(h)], dim=-1))
+    for i in range(1, n_hidden + 1):
+        z = act(lin(f'layers.{i}', z))
+    return lin('linear_out', z)
+
+
+def step_net(wl: 'Workload', net_fn: Callable[[Sequence[Tensor], Tensor], Tensor], leaves: Sequence[Tensor], groups: Dict[str, Tensor]):
+    """`step` for an arbitrary network function net_fn(leaves, x): streams, loss rows, total, d(total)/d(leaves)."""
+    leaves = [p.detach().clone().requires_grad_(True) for p in leaves]
+    imap = wl.index_map()
+    x_all = torch.cat(list(groups.values()))
+    order = max(len(i) for i in imap.values()) - 1
+    s_all = assign_derivs(autodiff_all(lambda z: net_fn(leaves, z), x_all, order), imap)
+    row_names, row_vals, type_sums = [], [], {}
+    start = 0
+    for gname, xg in groups.items():
+        sl = slice(start, start + xg.shape[0])
+        start += xg.shape[0]
+        o = {k: v[sl] for k, v in s_all.items()}
+        for loss_type, rname, r, w in wl.rows(gname, xg, o):
+            val = row_loss(r, w)
+            row_names.append(f'{loss_type}/{gname}/{rname}')
+            row_vals.append(val)
+            type_sums[loss_type] = type_sums.get(loss_type, 0.0) + val
+    total = wl.combine(type_sums)
+    grads = torch.autograd.grad(total, leaves)
+    return dict(streams={k: v.detach() for k, v in s_all.items()}, row_names=row_names,
+                rows=torch.stack(row_vals).detach(), total=total.detach(), grads=[g.detach() for g in grads])
+
+
 def init_mlp_params(d_in: int, n_out: int, width: int, n_act_layers: int, seed: int,
                     dtype=torch.float32) -> List[Tensor]:
     """Default nn.Linear init under torch.manual_seed(seed), in MLP construction order

@@ -113,7 +113,48 @@ CASES = [
 ]
 
 
+def fourier_case():
+    """AllenCahn tutorial network: Fourier_Net(2,1,100,4,RWF=True) (Tutorials/AllenCahn.py:65) on the Allen-Cahn loss table."""
+    from torch_DE.continuous.Networks import Fourier_Net
+    wl = O.WORKLOADS['allen_cahn']()
+    groups = O.sample_groups(wl, 64, 16, 16)
+    blob = {}
+    for tag, dtype in (('32', torch.float32), ('64', torch.float64)):
+        torch.manual_seed(1234)
+        net = Fourier_Net(2, 1, 100, 4, RWF=True).to(dtype)
+        names = [n for n, _ in net.named_parameters()]
+        if tag == '32':
+            for n, p_ in net.named_parameters():
+                blob['p_' + n] = p_.detach().numpy().copy()
+        dataset = PINN_dataset(wl.input_vars)
+        for gname, xg in groups.items():
+            dataset.add_group(gname, xg.to(dtype), batch_size=xg.shape[0])
+        batch = dataset[{g: torch.arange(x.shape[0]) for g, x in groups.items()}]
+        pinn = DE_Getter(net, wl.input_vars, wl.output_vars, list(wl.derivatives))
+        out = pinn.calculate(batch)
+        loss = reference_losses(wl, dataset)(batch, out)
+        total = combine(wl, loss.grouped_losses('loss_type'))
+        total.backward()
+        df = loss.get_DataFrame()
+        blob['row_names'] = np.array([f"{r['loss_type']}/{r['group']}/{r['variable']}" for _, r in df.iterrows()])
+        blob['rows' + tag] = torch.stack(list(df['aggregated_loss'])).detach().numpy()
+        blob['total' + tag] = total.detach().numpy()
+        for k, v in out['all'].items():
+            blob[f's{tag}_{k}'] = v.detach().numpy()
+        for n, p_ in net.named_parameters():
+            blob[f'g{tag}_{n}'] = p_.grad.detach().numpy().astype(np.float64 if tag == '64' else np.float32)
+        blob['names'] = np.array(list(pinn.derivatives.keys()))
+        blob['param_names'] = np.array(names)
+    blob['group_names'] = np.array(list(groups.keys()))
+    for g, x in groups.items():
+        blob['x_' + g] = x.numpy()
+    path = os.path.join(HERE, 'allen_cahn_fourier.npz')
+    np.savez_compressed(path, **blob)
+    print('allen_cahn_fourier total32', float(blob['total32']), 'total64', float(blob['total64']), os.path.getsize(path), 'bytes')
+
+
 def main():
+    fourier_case()
     for fixture, factory, n_col, n_bnd, seed, store_params in CASES:
         wl = factory()
         n = wl.net

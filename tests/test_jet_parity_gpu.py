@@ -327,3 +327,77 @@ def test_tensor_core_gradients_bitwise_repeatable():
     b = run_product('ldc')[-1]
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# RWF_Linear + Fourier_Embedding / Fourier_Net (Networks.py:25-75,104-120; AllenCahn.py:65, Stokes_Cylinder.py:84)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_fourier_net_rwf_matches_reference_golden(golden_dir):
+    import os
+    z = np.load(os.path.join(golden_dir, 'allen_cahn_fourier.npz'))
+    wl = WL.allen_cahn()
+    names = [str(n) for n in z['param_names']]
+    groups = {str(g): torch.from_numpy(z['x_' + str(g)]) for g in z['group_names']}
+    net = T.Fourier_Net(2, 1, 100, 4, RWF=True)
+    assert [n for n, _ in net.named_parameters()] == names          # same registration order as the reference
+    with torch.no_grad():
+        for n, p_ in net.named_parameters():
+            p_.copy_(torch.from_numpy(z['p_' + n]))
+    net = net.cuda()
+    pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+    batch = T.make_batch(wl.input_vars, {g: x.cuda() for g, x in groups.items()})
+    out = pinn.calculate(batch)
+    loss = wl.build_losses(list(groups.keys()))(batch, out)
+    total = wl.combine(loss.grouped_losses('loss_type'))
+    total.backward()
+    for k in pinn.derivatives:
+        got = out['all'][k].detach().cpu()
+        assert rel_l2(got, z['s64_' + k]) < TOL_STREAM, (k, rel_l2(got, z['s64_' + k]))
+        assert max_rel(got, z['s64_' + k]) < TOL_STREAM, k
+    assert abs(float(total) - float(z['total64'])) <= TOL_LOSS * abs(float(z['total64']))
+    for n, p_ in net.named_parameters():
+        assert rel_l2(p_.grad.cpu(), z['g64_' + n]) < TOL_LOSS, (n, rel_l2(p_.grad.cpu(), z['g64_' + n]))
+
+
+@pytest.mark.parametrize('cfg', [dict(d=2, m=3, w=128, h=3, act='sin', rwf=True), dict(d=3, m=3, w=64, h=2, act='tanh', rwf=True),
+                                 dict(d=2, m=1, w=256, h=2, act='tanh', rwf=False)])
+def test_fourier_net_variants_match_oracle(cfg):
+    from oracle import ref_autograd as O
+    torch.manual_seed(5)
+    net = T.Fourier_Net(cfg['d'], cfg['m'], cfg['w'], cfg['h'], activation=cfg['act'], RWF=cfg['rwf'], fourier_std=1.0)
+    ins, outs = ['x', 'y', 't'][:cfg['d']], ['u', 'v', 'p'][:cfg['m']]
+    ders = ['u_x', 'u_xx'] + (['u_y', 'u_yy'] if cfg['d'] >= 2 else [])
+    names = [n for n, _ in net.named_parameters()]
+    leaves = [p_.detach().clone().double() for _, p_ in net.named_parameters()]
+    x = torch.rand(97, cfg['d'], generator=torch.Generator().manual_seed(2))
+    imap = O.derivative_index_map(ins, outs, ders)
+    lv = [t.requires_grad_(True) for t in leaves]
+    ref = O.assign_derivs(O.autodiff_all(lambda zz: O.fourier_net_apply(dict(zip(names, lv)), zz, cfg['act'], cfg['h'], cfg['rwf']),
+                                         x.double(), 2), imap)
+    net = net.cuda()
+    pinn = T.DE_Getter(net, ins, outs, ders)
+    out = pinn(x.cuda())['all']
+    for k in imap:
+        assert rel_l2(out[k].detach().cpu(), ref[k].detach()) < TOL_STREAM, k
+    sum(v.pow(2).mean() for v in out.values()).backward()
+    gref = torch.autograd.grad(sum(v.pow(2).mean() for v in ref.values()), lv)
+    for (n, p_), g in zip(net.named_parameters(), gref):
+        assert rel_l2(p_.grad.cpu(), g) < TOL_LOSS, n
+
+
+def test_rwf_mlp_matches_plain_mlp_with_same_effective_weights():
+    torch.manual_seed(9)
+    rwf = T.MLP(2, 1, 64, 2, RWF=True).cuda()
+    plain = T.MLP(2, 1, 64, 2).cuda()
+    with torch.no_grad():
+        for a, b in zip(list(rwf.layers) + [rwf.linear_out], list(plain.layers) + [plain.linear_out]):
+            b.weight.copy_(a.v * a.s); b.bias.copy_(a.bias)
+    x = torch.rand(50, 2, device='cuda')
+    o1 = T.DE_Getter(rwf, ['x', 't'], ['u'], ['u_xx'])(x)['all']
+    o2 = T.DE_Getter(plain, ['x', 't'], ['u'], ['u_xx'])(x)['all']
+    for k in o1:
+        assert torch.allclose(o1[k], o2[k], rtol=1e-6, atol=1e-7)
+    o1['u_xx'].sum().backward(); o2['u_xx'].sum().backward()
+    for a, b in zip(list(rwf.layers) + [rwf.linear_out], list(plain.layers) + [plain.linear_out]):
+        assert rel_l2((a.v.grad * a.s).cpu() , (b.weight.grad * a.s * a.s).cpu()) < 1e-5     # dL/dv = dL/dW * s
+        assert rel_l2(a.s.grad.cpu(), (b.weight.grad * a.v).sum(1, keepdim=True).cpu()) < 1e-5

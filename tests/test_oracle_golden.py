@@ -61,3 +61,19 @@ def test_closed_form_single_neuron():
     assert torch.allclose(s['u'], v * t + c, atol=1e-6)
     assert torch.allclose(s['u_x'], v * w * (1 - t * t), atol=1e-6)
     assert torch.allclose(s['u_xx'], v * (-2 * w * w * t * (1 - t * t)), atol=1e-6)
+
+
+def test_oracle_fourier_net_matches_reference(golden_dir):
+    """Fourier_Net(2,1,100,4,RWF=True) on the Allen-Cahn loss table (Tutorials/AllenCahn.py:65)."""
+    import os
+    z = np.load(os.path.join(golden_dir, 'allen_cahn_fourier.npz'))
+    wl = O.WORKLOADS['allen_cahn']()
+    names = [str(n) for n in z['param_names']]
+    groups = {str(g): torch.from_numpy(z['x_' + str(g)]) for g in z['group_names']}
+    leaves = [torch.from_numpy(z['p_' + n]) for n in names]
+    res = O.step_net(wl, lambda lv, x: O.fourier_net_apply(dict(zip(names, lv)), x, 'tanh', 4, True), leaves, groups)
+    for k, s in res['streams'].items():
+        assert rel_l2(s, z['s32_' + k]) < 5e-6, k
+    assert abs(float(res['total']) - float(z['total32'])) <= 5e-6 * abs(float(z['total32']))
+    for n, g in zip(names, res['grads']):
+        assert rel_l2(g, z['g32_' + n]) < 2e-5, n

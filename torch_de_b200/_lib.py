@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtde_jet.so")
 
 ACT_NONE, ACT_TANH, ACT_SIN = 0, 1, 2
+ACT_FOURIER = 0x100
 MAX_LAYERS, MAX_IN, MAX_OUT, MAX_FIRST, MAX_SECOND = 24, 8, 4, 3, 6
 MAX_REGS, MAX_OPS, MAX_ROWS = 64, 128, 8
 (OP_CONST, OP_LOAD, OP_AUX, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_POWI, OP_ABS, OP_SIN, OP_COS, OP_DIV) = range(12)

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
                         }
                         zb[c] = a;
                     }
-                    act_backward<S, true>(p.act, st[pt], zb, hb[pt], z);
+                    act_backward<S, true>(layer_act(p.act, p.fourier_half, p.L - 1, n), st[pt], zb, hb[pt], z);
 #pragma unroll
                     for (int c = 0; c < J; ++c)
 #pragma unroll
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
                     float st[PT][J], z[PT][J];
                     load_stash_cols<S>(stash_prev + (size_t)(grp * PJ) * W + kb * kblk + r, W, st);
 #pragma unroll
-                    for (int pt = 0; pt < PT; ++pt) act_recompute<S>(p.act, st[pt], z[pt]);
+                    for (int pt = 0; pt < PT; ++pt) act_recompute<S>(layer_act(p.act, p.fourier_half, l - 1, kb * kblk + r), st[pt], z[pt]);
                     store_row_vec_b<S>(ubuf + (size_t)r * pitch + grp * PJ, z);
                 }
                 compute_sync();
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
                     float zb[J], zdummy[J];
 #pragma unroll
                     for (int c = 0; c < J; ++c) zb[c] = acc.get(pt * J + c, j);
-                    act_backward<S, false>(p.act, st[pt], zb, hb[pt], zdummy);
+                    act_backward<S, false>(layer_act(p.act, p.fourier_half, l - 1, n), st[pt], zb, hb[pt], zdummy);
                 }
                 if (active) store_row_vec_b<S>(A + (size_t)n * pitch + col0, hb);
             }

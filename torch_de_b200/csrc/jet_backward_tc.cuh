@@ -22,7 +22,7 @@ struct TcBwdParams {
     int64_t B;
     int64_t n_tiles;            // 16-point tiles
     int d_in, n_out, L, W, act, MB;
-    int n_stages, n_acc;
+    int n_stages, n_acc, fourier_half;
     int first_in[TDE_MAX_FIRST];
     const float* wct;           // transposed-weight chunk images [(L-1)][W/8][chunk]
     const float* w_out;         // [n_out][W] packed
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
 #pragma unroll
                                     for (int c = 0; c < J; ++c) zb[c] = zbg[q * J + c];
                                 }
-                                act_backward<S, true>(p.act, st, zb, hb, z);
+                                act_backward<S, true>(layer_act(p.act, p.fourier_half, l, n), st, zb, hb, z);
                                 db += hb[0];
                                 if (last) {
 #pragma unroll

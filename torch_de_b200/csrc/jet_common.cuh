@@ -105,6 +105,7 @@ struct JetParams {
     int d_in, n_out, L;  // L = number of ACTIVATED layers (>= 1)
     int W;               // padded hidden width (multiple of 64)
     int act;
+    int fourier_half;  // > 0: layer 0 is a Fourier embedding with this many frequencies (sin half, cos half)
     int PG;     // point groups per tile (tile points = PG * PT)
     int pitch;  // smem row pitch in floats (tile columns + pad, == 4 mod 8)
     int n_stages;
@@ -207,43 +208,66 @@ __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;"
 struct Sig {
     float s0, s1, s2, s3;
 };
-__device__ __forceinline__ Sig sig_from_pre(int act, float h0, float& stash0) {
+// activation codes: low nibble = outer function (TDE_ACT_TANH / TDE_ACT_SIN); kActInnerSin / kActInnerCos compose it with an
+// inner sin / cos -- the Fourier embedding layer of torch_DE's Fourier_Net is act(cat[sin(Wx), cos(Wx)]) (Networks.py:53-75,104-120).
+constexpr int kActInnerSin = 0x10;
+constexpr int kActInnerCos = 0x20;
+
+// sigma and its first three derivatives at v; `t_known`: v is already tanh(h) (the tanh stash) instead of h
+__device__ __forceinline__ Sig sig_plain(int outer, float v, bool t_known) {
     Sig s;
-    if (act == TDE_ACT_TANH) {
-        const float t = tanhf(h0);
+    if (outer == TDE_ACT_TANH) {
+        const float t = t_known ? v : tanhf(v);
         s.s0 = t;
         s.s1 = fmaf(-t, t, 1.0f);
         s.s2 = -2.0f * t * s.s1;
         s.s3 = -2.0f * s.s1 * fmaf(-3.0f * t, t, 1.0f);
-        stash0 = t;
     } else {
         float sn, cs;
-        sincosf(h0, &sn, &cs);
+        sincosf(v, &sn, &cs);
         s.s0 = sn;
         s.s1 = cs;
         s.s2 = -sn;
         s.s3 = -cs;
-        stash0 = h0;
     }
     return s;
 }
-__device__ __forceinline__ Sig sig_from_stash(int act, float st0) {
-    Sig s;
-    if (act == TDE_ACT_TANH) {
-        const float t = st0;
-        s.s0 = t;
-        s.s1 = fmaf(-t, t, 1.0f);
-        s.s2 = -2.0f * t * s.s1;
-        s.s3 = -2.0f * s.s1 * fmaf(-3.0f * t, t, 1.0f);
+// g = outer(inner(h)), inner = sin or cos: chain rule up to third order
+__device__ __forceinline__ Sig sig_composite(int act, float h0) {
+    float sn, cs;
+    sincosf(h0, &sn, &cs);
+    float i0, i1, i2, i3;
+    if (act & kActInnerSin) {
+        i0 = sn; i1 = cs; i2 = -sn; i3 = -cs;
     } else {
-        float sn, cs;
-        sincosf(st0, &sn, &cs);
-        s.s0 = sn;
-        s.s1 = cs;
-        s.s2 = -sn;
-        s.s3 = -cs;
+        i0 = cs; i1 = -sn; i2 = -cs; i3 = sn;
     }
+    const Sig o = sig_plain(act & 0xF, i0, false);
+    Sig g;
+    g.s0 = o.s0;
+    g.s1 = o.s1 * i1;
+    g.s2 = fmaf(o.s2 * i1, i1, o.s1 * i2);
+    g.s3 = fmaf(o.s3 * i1 * i1, i1, fmaf(3.0f * o.s2 * i1, i2, o.s1 * i3));
+    return g;
+}
+// what the stash keeps in channel 0: tanh keeps t = tanh(h0); sin and the composite activations keep h0 itself
+__device__ __forceinline__ Sig sig_from_pre(int act, float h0, float& stash0) {
+    if (act & (kActInnerSin | kActInnerCos)) {
+        stash0 = h0;
+        return sig_composite(act, h0);
+    }
+    const Sig s = sig_plain(act, h0, false);
+    stash0 = act == TDE_ACT_TANH ? s.s0 : h0;
     return s;
+}
+__device__ __forceinline__ Sig sig_from_stash(int act, float st0) {
+    if (act & (kActInnerSin | kActInnerCos)) return sig_composite(act, st0);
+    return sig_plain(act, st0, true);
+}
+// activation of neuron n of activated layer l: layer 0 of a Fourier_Net is the embedding (first half sin, second half cos)
+__device__ __forceinline__ int layer_act(int act, int fourier_half, int l, int n) {
+    if (l != 0 || fourier_half == 0) return act;
+    return act | (n < fourier_half ? kActInnerSin : kActInnerCos);
 }
 
 // z = act-jet(h); h[0] is replaced by the value to stash (t or h0); h[c>0] unchanged (they are stashed as is)

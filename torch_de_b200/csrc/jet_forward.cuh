@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_forward_kernel(const __grid_c
                     for (int a = 0; a < NF; ++a) h[1 + a] = wf[a];
 #pragma unroll
                     for (int q = 0; q < S::NS; ++q) h[1 + NF + q] = 0.0f;
-                    act_forward<S>(p.act, h, zt[pt]);
+                    act_forward<S>(layer_act(p.act, p.fourier_half, 0, n), h, zt[pt]);
 #pragma unroll
                     for (int c = 0; c < J; ++c) st[pt][c] = h[c];
                 }

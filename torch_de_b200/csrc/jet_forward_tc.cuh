@@ -27,6 +27,7 @@ struct TcParams {
     int64_t n_tiles;       // 16-point tiles
     int d_in, n_out, L, W, act, MB;   // MB = W / 128
     int n_stages;
+    int fourier_half;      // > 0: layer 0 is a Fourier embedding (sin half | cos half)
     long long* dbg_buf;    // optional cycle stamps (TDE_TC_DBG bit 2)
     int dbg;               // bit0: skip weight streaming (timing experiment only)
     int n_acc;             // TMEM accumulator sets: 3 = {small terms, main even k-steps, main odd k-steps}, 2, or 1
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                                     for (int c = 0; c < J; ++c) h[c] = hg[q * J + c];
                                     h[0] += bn;
                                 }
-                                act_forward<S>(p.act, h, z);      // h[0] now holds the value to stash (t | h0)
+                                act_forward<S>(layer_act(p.act, p.fourier_half, l, n), h, z);      // h[0] now holds the value to stash (t | h0)
 #pragma unroll
                                 for (int c = 0; c < J; ++c) {
                                     const int col8 = pt8 * J + c;           // column within this half (compile-time)

@@ -83,7 +83,7 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 // Everything derived from (net, spec, n_points): geometry + workspace offsets (in floats).
 struct Geometry {
     int nf, smask, J, PT, PJ;
-    int width, W, L, d_in, n_out, act;
+    int width, W, L, d_in, n_out, act, fourier_half;
     int PG, TP, pitch, stages_fwd, stages_bwd, kblk, rsplit;
     int smem_fwd, smem_bwd;
     int n_ctas;
@@ -124,7 +124,8 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         return fail("need 2..%d Linear layers, got %d", TDE_MAX_LAYERS, net->n_layers);
     const int L = net->n_layers - 1;
     const int width = net->layers[0].out_features;
-    const int act = net->layers[0].act;
+    const int fourier = net->layers[0].act & TDE_ACT_FOURIER;
+    const int act = net->layers[0].act & ~TDE_ACT_FOURIER;
     if (act != TDE_ACT_TANH && act != TDE_ACT_SIN) return fail("unsupported activation code %d (tanh/sin only)", act);
     if (net->layers[0].in_features != spec->d_in) return fail("layer 0 in_features %d != d_in %d", net->layers[0].in_features, spec->d_in);
     if (spec->d_in < 1 || spec->d_in > TDE_MAX_IN) return fail("d_in %d out of range 1..%d", spec->d_in, TDE_MAX_IN);
@@ -134,7 +135,8 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         if (!ly.weight || !ly.bias) return fail("layer %d: weight and bias are required", l);
         if (l < L) {
             if (ly.out_features != width) return fail("hidden widths must all be equal (layer %d has %d, expected %d)", l, ly.out_features, width);
-            if (ly.act != act) return fail("all hidden activations must match");
+            if ((ly.act & ~TDE_ACT_FOURIER) != act) return fail("all hidden activations must match");
+            if (l > 0 && (ly.act & TDE_ACT_FOURIER)) return fail("only the first layer can be a Fourier embedding");
             if (l > 0 && ly.in_features != width) return fail("layer %d in_features %d != width %d", l, ly.in_features, width);
         } else {
             if (ly.act != TDE_ACT_NONE) return fail("last layer must be linear");
@@ -169,6 +171,8 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.d_in = spec->d_in;
     g.n_out = spec->n_out;
     g.act = act;
+    if (fourier && (width & 1)) return fail("a Fourier embedding needs an even hidden width");
+    g.fourier_half = fourier ? width / 2 : 0;
     g.W = width <= 256 ? (int)align_up(width, 64) : (int)align_up(width, 256);
     if (g.W > 2048) return fail("hidden width %d too large (max 2048)", width);
     const int NG = g.W / tde::kNT;
@@ -394,7 +398,7 @@ int launch_pack(const TdeNet* net, const Geometry& g, float* ws, bool want_wt, b
 
 void fill_params(const Geometry& g, const TdeJetSpec* spec, float* ws, tde::JetParams* p) {
     memset(p, 0, sizeof *p);
-    p->d_in = g.d_in; p->n_out = g.n_out; p->L = g.L; p->W = g.W; p->act = g.act;
+    p->d_in = g.d_in; p->n_out = g.n_out; p->L = g.L; p->W = g.W; p->act = g.act; p->fourier_half = g.fourier_half;
     p->PG = g.PG; p->pitch = g.pitch; p->n_tiles = g.n_tiles;
     for (int a = 0; a < TDE_MAX_FIRST; ++a) p->first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
     p->w_in = ws + g.o_w_in; p->b_in = ws + g.o_b_in; p->wt_hidden = ws + g.o_wt; p->wn_hidden = ws + g.o_wn;
@@ -671,7 +675,7 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
     if (g.use_tc) {
         tde::TcParams t{};
         t.x = x; t.B = n_points; t.n_tiles = g.tc_tiles;
-        t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb; t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc;
+        t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb; t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc; t.fourier_half = g.fourier_half;
         { const char* d = getenv("TDE_TC_DBG"); t.dbg = d ? atoi(d) : 0; }
         static long long* dbg_buf = nullptr;
         if (t.dbg & 4) {
@@ -725,7 +729,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         tde::TcBwdParams t{};
         t.x = x; t.B = n_points; t.n_tiles = g.tc_tiles;
         t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb;
-        t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc;
+        t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc; t.fourier_half = g.fourier_half;
         for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
         t.wct = ws + g.o_wct; t.w_out = ws + g.o_wo;
         t.seeds = seeds; t.ld_seeds = ld_seeds; t.stash = stash;

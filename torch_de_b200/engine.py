@@ -38,12 +38,11 @@ class JetRunner:
     """Binds one network + one channel layout to the C ABI: builds the TdeNet/TdeJetSpec structs,
     sizes and caches stash/workspace, launches forward / backward."""
 
-    def __init__(self, lins: Sequence[torch.nn.Linear], act: int, channels: JetChannels):
-        self.lins = list(lins)
+    def __init__(self, lins, act: int, channels: JetChannels):
+        self.lins = list(lins)                  # LayerSpec per Linear-like layer
         self.act = act
         self.ch = channels
-        self.params: List[torch.nn.Parameter] = [p for lin in self.lins for p in (lin.weight, lin.bias)]
-        self.n_params = sum(p.numel() for p in self.params)
+        self.n_params = sum(sp.in_features * sp.out_features + sp.out_features for sp in self.lins)
         self._spec = _lib.TdeJetSpec()
         s = self._spec
         s.d_in, s.n_out, s.n_first, s.n_second = channels.d_in, channels.n_out, channels.n_first, len(channels.pairs)
@@ -66,16 +65,25 @@ class JetRunner:
             ly = self._net.layers[l]
             ly.weight, ly.bias = w.data_ptr(), b.data_ptr()
             ly.in_features, ly.out_features = lin.in_features, lin.out_features
-            ly.act = self.act if l < n - 1 else _lib.ACT_NONE
+            ly.act = (self.act | (_lib.ACT_FOURIER if lin.fourier else 0)) if l < n - 1 else _lib.ACT_NONE
 
     def plan(self, n_points: int) -> _lib.TdePlan:
         p = self._plans.get(n_points)
         if p is None:
-            self._bind([t for t in self.params])
+            with torch.no_grad():
+                self._bind(self.effective_tensors())
             p = _lib.TdePlan()
             _lib.check(_lib.lib().tde_plan(C.byref(self._net), C.byref(self._spec), n_points, C.byref(p)), "tde_plan")
             self._plans[n_points] = p
         return p
+
+    def effective_tensors(self) -> List[torch.Tensor]:
+        """[W0, b0, W1, b1, ...] as the kernels consume them (autograd-tracked functions of the leaf parameters)."""
+        out = []
+        for sp in self.lins:
+            w, b = sp.tensors()
+            out += [w.contiguous(), b.contiguous()]
+        return out
 
     def _ws(self, nbytes: int, device) -> torch.Tensor:
         if self._workspace is None or self._workspace.numel() * 4 < nbytes or self._workspace.device != device:
@@ -93,7 +101,7 @@ class JetRunner:
             raise ValueError(f"input must be [B, {self.ch.d_in}], got {tuple(x.shape)}")
         if x.dtype != torch.float32:
             raise TypeError("input must be float32")
-        for p in self.params:
+        for p in self.lins[0].module.parameters():
             if p.device != x.device:
                 raise RuntimeError(f"network parameters live on {p.device} but the input is on {x.device}")
         return x.contiguous()
@@ -138,9 +146,11 @@ class JetRunner:
 
     def split_flat(self, flat: torch.Tensor) -> List[torch.Tensor]:
         views, o = [], 0
-        for p in self.params:
-            views.append(flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
+        for sp in self.lins:
+            for shape in ((sp.out_features, sp.in_features), (sp.out_features,)):
+                n = shape[0] * (shape[1] if len(shape) > 1 else 1)
+                views.append(flat[o:o + n].view(shape))
+                o += n
         return views
 
 
@@ -231,7 +241,7 @@ class Jet_engine(_EngineBase):
 
     # -- helpers -----------------------------------------------------------------------------
     def _jets(self, runner: JetRunner, x: torch.Tensor) -> torch.Tensor:
-        return _JetFunction.apply(x, runner, *runner.params)
+        return _JetFunction.apply(x, runner, *runner.effective_tensors())
 
     def _named(self, runner: JetRunner, block: torch.Tensor, names, lo=None, hi=None) -> Dict[str, torch.Tensor]:
         if lo is None:
