@@ -8,7 +8,7 @@ from typing import Sequence
 
 import torch
 
-from .engine import Jet_engine, _EngineBase
+from .engine import FD_engine, Jet_engine, _EngineBase
 from .networks import extract_layers
 from .spec import derivative_index_map
 
@@ -53,8 +53,11 @@ class DE_Getter:
         if isinstance(deriv_method, str):
             if deriv_method in ('jet', 'AD'):      # 'AD' keeps tutorial scripts working; it selects the jet kernels
                 self.deriv_method = Jet_engine(self.net, self.derivatives, **kwargs)
+            elif deriv_method == 'FD':
+                kwargs.setdefault('dxs', [1e-3 for _ in range(len(self.input_vars))])      # DE_module.py:138
+                self.deriv_method = FD_engine(self.net, self.derivatives, **kwargs)
             else:
-                raise NotImplementedError(f"derivative method '{deriv_method}' is not built (jet only; FD is SURVEY 8f)")
+                raise NotImplementedError(f"derivative method '{deriv_method}' does not exist ('jet' | 'AD' | 'FD')")
         elif isinstance(deriv_method, _EngineBase) or hasattr(deriv_method, 'calculate'):
             self.deriv_method = deriv_method
         else:
