@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_backward_kernel(const __grid_
     for (int i = tid; i < p.n_out * W; i += kComputeThreads) wout_s[i] = p.w_out[i];
 
     float* gp = p.gpart + (size_t)blockIdx.x * p.gp_stride;
-    const size_t stash_layer_stride = (size_t)p.n_tiles * W * TPJ;
+    const size_t stash_layer_stride = (size_t)p.stash_layer_stride;
 
     int cs = 0;        // consumer position in the stage ring
     uint32_t cph = 0;  // and its phase

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
     unsigned char* const smem_raw = smem_tc;
 
     constexpr int MB = W / 128;
+    constexpr int kAccSets = tc_acc_sets(MB, N);
     const int n_stages = p.n_stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
     uint64_t* acc_ready = act_ready + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
     unsigned char* zhi = smem_raw + 1024;
-    const uint32_t z_plane = (uint32_t)(W / 32) * ATOMK;
+    constexpr uint32_t z_plane_c = (uint32_t)(W / 32) * ATOMK;
+    const uint32_t z_plane = z_plane_c;
     unsigned char* zlo = zhi + z_plane;
     const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;
     unsigned char* wst = zlo + z_plane;
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
             const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
             const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
             const uint32_t stage_step = chunk_bytes >> 4, blk_step = 4096u >> 4;
-            const int n_acc = p.n_acc;
+            constexpr int n_acc = kAccSets;
             int s = 0;
             uint32_t ph = 0, act_ph = 0;
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
@@ -186,8 +188,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
 
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
                 const bool first = pair == first_pair;
+                // the second tile of the last pair may be padding (>= n_tiles): x = 0 and seeds = 0 there and the streams have
+                // rows for it, so it runs the same code and contributes exact zeros
                 const int64_t tile = pair * kTcCluster + crank;
-                const bool real = tile < p.n_tiles;
                 const int64_t pbase = tile * kTcPoints;
                 for (int i = et; i < kTcPoints * p.d_in; i += n_epi) {
                     const int64_t gpt = pbase + i / p.d_in;
@@ -199,47 +202,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                     seeds_s[i] = gpt < p.B ? p.seeds[(size_t)r * p.ld_seeds + gpt] : 0.0f;
                 }
                 epi_sync();
-                size_t row0 = 0;
-                if (real) {
-                    const int64_t bw_tile = tile / p.tiles_per_bw_tile;
-                    const int sub = (int)(tile - bw_tile * p.tiles_per_bw_tile);
-                    row0 = ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N) * W + n;
-                }
+                const size_t row0 = (size_t)tile * N * W + n;     // [layer][tile][jet column][neuron]
 
                 // Epilogue as 2 x (2 steps of 4 points): 8 points are unrolled so every shared/global offset is an immediate (a
-                // 16-point unroll is >200 KB of code and instruction-cache bound).  The stash values and the TMEM accumulators
-                // of the NEXT 4-point step are requested before the current step is processed.
+                // 16-point unroll is >200 KB of code and instruction-cache bound).  The stash values of the NEXT 4-point step
+                // are requested before the current step is processed; TMEM is read where it is used (12-cycle latency).
+                // Base addresses pass through empty asm statements: otherwise the compiler, short of registers, re-derives
+                // every one of the 240 addresses of a layer from the kernel parameters (10 instructions per store).
                 constexpr int GC = kTcGroup * J;
                 float wo[TDE_MAX_OUT];
 #pragma unroll
                 for (int o = 0; o < TDE_MAX_OUT; ++o) wo[o] = o < p.n_out ? wout_s[o * W + n] : 0.0f;
-                uint32_t xorv[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) xorv[j] = zrow + ((kchunk ^ (uint32_t)j) << 4);
 
                 // The body is instantiated three times (last hidden layer: adjoint seeded from the output layer; middle layers;
                 // input layer) so the hot middle-layer code carries none of the special-case registers or branches.
                 auto layer_body = [&](auto kind_c, const int l) {
                     constexpr int KIND = decltype(kind_c)::value;     // 2 last, 1 middle, 0 input layer
                     constexpr bool last = KIND == 2;
-                    const float* srow = p.stash + (size_t)l * p.stash_layer_stride + row0;
-                    float* hrow = p.hbar + (size_t)l * p.stash_layer_stride + row0;
-                    float* zrow_g = p.zst + (size_t)l * p.stash_layer_stride + row0;
+                    const size_t loff = (size_t)l * p.stash_layer_stride + row0;
+                    const float* srow_h = p.stash + loff;
+                    float* hrow_h = p.hbar + loff;
+                    float* zrow_h = p.zst + loff;
+                    uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) zaddr[j] = smem_u32(zhi) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u;
                     const bool stamp = p.dbg_buf && blockIdx.x == 0 && n == 0 && tile == 0 && l == 3;
                     if (stamp) p.dbg_buf[0] = clock64();
                     float st_next[GC];
 #pragma unroll
-                    for (int i = 0; i < GC; ++i) st_next[i] = real ? __ldcs(srow + (size_t)i * W) : 0.0f;
+                    for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)i * W);
                     uint32_t taddr = 0;
-                    float cur[3][GC];
                     if (!last) {
                         mbar_wait(acc_ready, acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
                         taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
-#pragma unroll
-                        for (int a = 0; a < 3; ++a)
-                            if (a < p.n_acc) tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N), cur[a]);
                     }
                     if (stamp) p.dbg_buf[1] = clock64();
                     float db = 0.0f;
@@ -248,16 +245,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                     for (int o = 0; o < TDE_MAX_OUT; ++o) dwo[o] = 0.0f;
 #pragma unroll
                     for (int i = 0; i < TDE_MAX_IN; ++i) dw_in[i] = 0.0f;
-                    if (stamp) p.dbg_buf[2] = clock64();
+                    const float* xs_h = xs;
+                    const float* seeds_h = seeds_s;
 #pragma unroll 1
                     for (int half = 0; half < 2; ++half) {
-                        unsigned char* zhi_h = zhi + (uint32_t)half * (uint32_t)(J * 1024);
-                        unsigned char* zlo_h = zlo + (uint32_t)half * (uint32_t)(J * 1024);
-                        const float* srow_h = srow + (size_t)half * (8 * J) * W;
-                        float* hrow_h = hrow + (size_t)half * (8 * J) * W;
-                        float* zrow_h = zrow_g + (size_t)half * (8 * J) * W;
-                        const float* xs_h = xs + half * 8 * p.d_in;
-                        const float* seeds_h = seeds_s + half * 8;
+                        asm volatile("" : "+l"(srow_h), "+l"(hrow_h), "+l"(zrow_h));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
 #pragma unroll
                         for (int g2 = 0; g2 < 2; ++g2) {
                             float stg[GC], zbg[GC];
@@ -265,25 +259,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                             for (int i = 0; i < GC; ++i) stg[i] = st_next[i];
                             if (g2 == 0) {
 #pragma unroll
-                                for (int i = 0; i < GC; ++i) st_next[i] = real ? __ldcs(srow_h + (size_t)(GC + i) * W) : 0.0f;
+                                for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)(GC + i) * W);
                             } else if (half == 0) {
 #pragma unroll
-                                for (int i = 0; i < GC; ++i) st_next[i] = real ? __ldcs(srow_h + (size_t)(2 * GC + i) * W) : 0.0f;
+                                for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)(2 * GC + i) * W);
                             }
                             if (!last) {
+                                float cur[kAccSets][GC];
+#pragma unroll
+                                for (int a = 0; a < kAccSets; ++a) tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + g2 * GC), cur[a]);
                                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                                 for (int i = 0; i < GC; ++i) {
                                     float v = cur[0][i];
-                                    if (p.n_acc > 1) v += cur[1][i];
-                                    if (p.n_acc > 2) v += cur[2][i];
-                                    zbg[i] = v;
-                                }
-                                if (half * 2 + g2 + 1 < kTcPoints / kTcGroup) {
 #pragma unroll
-                                    for (int a = 0; a < 3; ++a)
-                                        if (a < p.n_acc)
-                                            tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + (half * 2 + g2 + 1) * GC), cur[a]);
+                                    for (int a = 1; a < kAccSets; ++a) v += cur[a][i];
+                                    zbg[i] = v;
                                 }
                             }
 #pragma unroll
@@ -318,12 +309,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
 #pragma unroll
                                     for (int c = 0; c < J; ++c) {
                                         const int col8 = pt8 * J + c;
-                                        if (real) __stcs(hrow_h + (size_t)col8 * W, hb[c]);
-                                        const uint32_t off = (uint32_t)(col8 >> 3) * 1024u + (uint32_t)(col8 & 7) * 128u + xorv[col8 & 7];
+                                        __stcs(hrow_h + (size_t)col8 * W, hb[c]);
                                         float hi, lo;
                                         split_tf32(hb[c], hi, lo);
-                                        *reinterpret_cast<float*>(zhi_h + off) = hi;
-                                        *reinterpret_cast<float*>(zlo_h + off) = lo;
+                                        const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
+                                        sts_f32(a, hi);
+                                        sts_f32(a + z_plane_c, lo);
                                     }
                                 } else {
                                     // input layer: h = W0 x + b0, h_a = W0[:, first_in[a]]
@@ -338,12 +329,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                                             if (i == p.first_in[a]) dw_in[i] += hb[1 + a];
                                     }
                                 }
-                                if (KIND != 2 && real) {
+                                if constexpr (KIND != 2) {
 #pragma unroll
                                     for (int c = 0; c < J; ++c) __stcs(zrow_h + (size_t)(pt8 * J + c) * W, z[c]);
                                 }
                             }
                         }
+                        srow_h += (size_t)(8 * J) * W;
+                        hrow_h += (size_t)(8 * J) * W;
+                        zrow_h += (size_t)(8 * J) * W;
+                        taddr += 2 * GC;
+                        xs_h += 8 * p.d_in;
+                        seeds_h += 8;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) zaddr[j] += (uint32_t)(J * 1024);
                     }
                     if (stamp) p.dbg_buf[3] = clock64();
                     if constexpr (KIND >= 1) {

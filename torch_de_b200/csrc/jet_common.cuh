@@ -102,6 +102,7 @@ struct JetParams {
     const float* x;  // [B][d_in]
     int64_t B;
     int64_t n_tiles;
+    int64_t stash_layer_stride;  // floats between layers of the stash (>= n_tiles * W * TP * J)
     int d_in, n_out, L;  // L = number of ACTIVATED layers (>= 1)
     int W;               // padded hidden width (multiple of 64)
     int act;
@@ -338,9 +339,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// cvt.rna.tf32.f32 compiles to 4 instructions (it also handles NaN/Inf); for the finite values on this path the same
+// rounding is an integer add of half a TF32 ulp and a mask.  The tensor core ignores the 13 low mantissa bits of a TF32
+// operand, so the low part only needs the add (its mask is applied by the hardware).
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = tf32_rna(x);
-    lo = tf32_rna(x - hi);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) + 0x1000u);
 }
 
 // packed FP32 pairs (Blackwell fma.rn.f32x2: two FMAs per issue slot and per register-file read)

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) jet_forward_kernel(const __grid_c
         compute_sync();
 
         float* stash_tile = p.stash ? p.stash + (size_t)tile * W * (TP * J) : nullptr;
-        const size_t stash_layer_stride = (size_t)p.n_tiles * W * (TP * J);
+        const size_t stash_layer_stride = (size_t)p.stash_layer_stride;
 
         // ---- input layer (K = d_in): jets of an affine map are its columns ----
         {

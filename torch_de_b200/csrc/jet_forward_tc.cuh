@@ -176,6 +176,9 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
     }
 }
 constexpr int kTcGroup = 4;        // points handled per unrolled epilogue step (16 points = 4 steps)
+// accumulator sets that fit the 512 TMEM columns (3: cross terms | main even k-steps | main odd k-steps)
+__host__ __device__ constexpr int tc_acc_sets(int mb, int n) { return 512 / (mb * n) >= 3 ? 3 : 512 / (mb * n); }
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 template <int NF, int SMASK, int W>
 __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __grid_constant__ TcParams p) {
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     unsigned char* const smem_raw = smem_tc;
 
     constexpr int MB = W / 128;
+    constexpr int kAccSets = tc_acc_sets(MB, N);
     const int n_stages = p.n_stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
@@ -196,7 +200,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     uint64_t* acc_ready = act_ready + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
     unsigned char* zhi = smem_raw + 1024;
-    const uint32_t z_plane = (uint32_t)(W / 32) * ATOMK;
+    constexpr uint32_t z_plane_c = (uint32_t)(W / 32) * ATOMK;
+    const uint32_t z_plane = z_plane_c;
     unsigned char* zlo = zhi + z_plane;
     const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;   // [hi|lo][mb][kgroup 2][16 row groups][8][4] floats*4
     unsigned char* wst = zlo + z_plane;                              // [n_stages][chunk_bytes]
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
             const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
             const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
             const uint32_t stage_step = chunk_bytes >> 4, blk_step = 4096u >> 4;
-            const int n_acc = p.n_acc;
+            constexpr int n_acc = kAccSets;
             int s = 0;
             uint32_t ph = 0, act_ph = 0;
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
@@ -332,35 +337,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
             uint32_t acc_ph = 0;
 
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
-                const int64_t tile = pair * kTcCluster + crank;     // may be a dummy tile (>= n_tiles): nothing is written
+                const int64_t tile = pair * kTcCluster + crank;     // may be a padding tile (>= n_tiles, all points >= B)
                 const int64_t pbase = tile * kTcPoints;
                 for (int i = et; i < kTcPoints * p.d_in; i += n_epi) {
                     const int64_t gp = pbase + i / p.d_in;
                     xs[i] = gp < p.B ? p.x[gp * p.d_in + (i % p.d_in)] : 0.0f;
                 }
                 epi_sync();
-                float* stash_row = nullptr;
-                if (p.stash && tile < p.n_tiles) {
-                    const int64_t bw_tile = tile / p.tiles_per_bw_tile;
-                    const int sub = (int)(tile - bw_tile * p.tiles_per_bw_tile);
-                    // [layer][backward tile][jet column][neuron]: this thread's neuron, first column of its 16-point sub-tile
-                    stash_row = p.stash + ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N) * W + n;
-                }
+                // [layer][tile][jet column][neuron]: this thread's neuron, first column of the tile.  A padding tile (the second
+                // tile of the last pair when the tile count is odd) has stash rows of its own and x = 0.
+                float* const stash_row = p.stash ? p.stash + (size_t)tile * N * W + n : nullptr;
 
                 // Per layer the epilogue walks the 16 points as 2 x (2 steps of 4 points): 8 points are unrolled so every
-                // shared/global offset is an immediate (a 16-point unroll is >80 KB of code and instruction-cache bound),
-                // and the TMEM columns of the next 4-point step are requested before the current step is used.
+                // shared/global offset is an immediate (a 16-point unroll is >80 KB of code and instruction-cache bound).
+                // Base addresses pass through empty asm statements so the compiler keeps them in registers instead of
+                // re-deriving each store address from the kernel parameters.
                 constexpr int GC = kTcGroup * J;          // jet columns per 4-point step
-                uint32_t xorv[8];                         // swizzled 16 B chunk offset for each (column & 7)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) xorv[j] = zrow + ((kchunk ^ (uint32_t)j) << 4);
-                auto layer_body = [&](auto first_c, const int l) {
+                auto layer_body = [&](auto first_c, auto stash_c, const int l) {
                     constexpr bool kFirst = decltype(first_c)::value;     // input layer (no GEMM) vs hidden layers
-                    float* srow = stash_row ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
+                    constexpr bool kStash = decltype(stash_c)::value;
+                    float* srow_h = kStash ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
+                    uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) zaddr[j] = smem_u32(zhi) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u;
                     float wrow[TDE_MAX_IN], wf[NF > 0 ? NF : 1];
                     float bn;
                     uint32_t taddr = 0;
-                    float cur[3][GC];
                     if constexpr (kFirst) {
 #pragma unroll
                         for (int i = 0; i < TDE_MAX_IN; ++i) wrow[i] = i < p.d_in ? __ldg(p.w_in + n * p.d_in + i) : 0.0f;
@@ -373,33 +375,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                         acc_ph ^= 1;
                         tc_fence_after();
                         taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
-#pragma unroll
-                        for (int a = 0; a < 3; ++a)
-                            if (a < p.n_acc) tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N), cur[a]);
                     }
+                    const float* xs_h = xs;
 #pragma unroll 1
                     for (int half = 0; half < 2; ++half) {
-                        unsigned char* zhi_h = zhi + (uint32_t)half * (uint32_t)(J * 1024);   // 8 points = J column groups of 8
-                        unsigned char* zlo_h = zlo + (uint32_t)half * (uint32_t)(J * 1024);
-                        float* srow_h = srow ? srow + (size_t)half * (8 * J) * W : nullptr;
-                        const float* xs_h = xs + half * 8 * p.d_in;
+                        if constexpr (kStash) asm volatile("" : "+l"(srow_h));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
 #pragma unroll
                         for (int g2 = 0; g2 < 2; ++g2) {
                             float hg[GC];
                             if constexpr (!kFirst) {
+                                float cur[kAccSets][GC];
+#pragma unroll
+                                for (int a = 0; a < kAccSets; ++a) tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + g2 * GC), cur[a]);
                                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                                 for (int i = 0; i < GC; ++i) {
                                     float v = cur[0][i];
-                                    if (p.n_acc > 1) v += cur[1][i];
-                                    if (p.n_acc > 2) v += cur[2][i];
-                                    hg[i] = v;
-                                }
-                                if (half * 2 + g2 + 1 < kTcPoints / kTcGroup) {
 #pragma unroll
-                                    for (int a = 0; a < 3; ++a)
-                                        if (a < p.n_acc)
-                                            tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + (half * 2 + g2 + 1) * GC), cur[a]);
+                                    for (int a = 1; a < kAccSets; ++a) v += cur[a][i];
+                                    hg[i] = v;
                                 }
                             }
 #pragma unroll
@@ -425,15 +421,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
 #pragma unroll
                                 for (int c = 0; c < J; ++c) {
                                     const int col8 = pt8 * J + c;           // column within this half (compile-time)
-                                    if (srow_h) __stcs(srow_h + (size_t)col8 * W, h[c]);      // one 128 B line per warp store
-                                    const uint32_t off = (uint32_t)(col8 >> 3) * 1024u + (uint32_t)(col8 & 7) * 128u + xorv[col8 & 7];
+                                    if constexpr (kStash) __stcs(srow_h + (size_t)col8 * W, h[c]);      // one 128 B line per warp store
                                     float hi, lo;
                                     split_tf32(z[c], hi, lo);
-                                    *reinterpret_cast<float*>(zhi_h + off) = hi;
-                                    *reinterpret_cast<float*>(zlo_h + off) = lo;
+                                    const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
+                                    sts_f32(a, hi);
+                                    sts_f32(a + z_plane_c, lo);
                                 }
                             }
                         }
+                        if constexpr (kStash) srow_h += (size_t)(8 * J) * W;
+                        taddr += 2 * GC;
+                        xs_h += 8 * p.d_in;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) zaddr[j] += (uint32_t)(J * 1024);   // 8 points = J column groups of 8
                     }
                     if (l < p.L - 1) {
                         // publish: smem writes -> async proxy, TMEM reads retired, then one arrive per warp
@@ -443,8 +444,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                         if (lane == 0) mbar_arrive(act_ready);
                     }
                 };
-                layer_body(std::true_type{}, 0);
-                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, l);
+                if (stash_row) {
+                    layer_body(std::true_type{}, std::true_type{}, 0);
+                    for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::true_type{}, l);
+                } else {
+                    layer_body(std::true_type{}, std::false_type{}, 0);
+                    for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::false_type{}, l);
+                }
                 epi_sync();   // every neuron's last-layer z is in the planes
 
                 // ---- output layer: one thread per jet column, z = hi + lo ----

@@ -99,7 +99,7 @@ struct Geometry {
     int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo, gp_stride;
     int64_t o_gpart;
     int64_t workspace_floats;
-    int64_t stash_floats;
+    int64_t stash_floats, stash_layer_stride;
     int64_t n_params;
     const Dispatch* disp;
 };
@@ -268,7 +268,14 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.g_bo = q;     q = align_up(q + g.n_out, 4);
     g.gp_stride = q;
     g.o_gpart = g.packed_floats;
-    g.stash_floats = (int64_t)L * g.n_tiles * g.W * g.TP * g.J;
+    // The tcgen05 kernels walk 16-point tiles in cluster pairs: when the tile count is odd the last pair's second tile is
+    // padding (x = 0, seeds = 0) and needs real stash rows behind it.
+    g.stash_layer_stride = g.n_tiles * g.W * (int64_t)g.TP * g.J;
+    if (g.use_tc) {
+        const int64_t padded = (g.tc_tiles + tde::kTcCluster - 1) / tde::kTcCluster * tde::kTcCluster;
+        g.stash_layer_stride = std::max<int64_t>(g.stash_layer_stride, padded * tde::kTcPoints * (int64_t)g.J * g.W);
+    }
+    g.stash_floats = (int64_t)L * g.stash_layer_stride;
     g.workspace_floats = align_up(g.packed_floats + (int64_t)std::max(g.n_ctas, sm_count()) * g.gp_stride, 64);
     g.o_hbar = g.o_zst = 0;
     if (g.use_tc_bwd) {       // Hbar_l and Z_l streams for the tensor-core weight-gradient kernel
@@ -399,7 +406,7 @@ int launch_pack(const TdeNet* net, const Geometry& g, float* ws, bool want_wt, b
 void fill_params(const Geometry& g, const TdeJetSpec* spec, float* ws, tde::JetParams* p) {
     memset(p, 0, sizeof *p);
     p->d_in = g.d_in; p->n_out = g.n_out; p->L = g.L; p->W = g.W; p->act = g.act; p->fourier_half = g.fourier_half;
-    p->PG = g.PG; p->pitch = g.pitch; p->n_tiles = g.n_tiles;
+    p->PG = g.PG; p->pitch = g.pitch; p->n_tiles = g.n_tiles; p->stash_layer_stride = g.stash_layer_stride;
     for (int a = 0; a < TDE_MAX_FIRST; ++a) p->first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
     p->w_in = ws + g.o_w_in; p->b_in = ws + g.o_b_in; p->wt_hidden = ws + g.o_wt; p->wn_hidden = ws + g.o_wn;
     p->b_hidden = ws + g.o_bh; p->w_out = ws + g.o_wo; p->b_out = ws + g.o_bo;
@@ -686,7 +693,7 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
         t.w_in = ws + g.o_w_in; t.b_in = ws + g.o_b_in; t.wc = ws + g.o_wc; t.b_hidden = ws + g.o_bh;
         t.w_out = ws + g.o_wo; t.b_out = ws + g.o_bo;
         t.out = out; t.ld_out = ld_out; t.stash = stash;
-        t.stash_layer_stride = g.n_tiles * g.W * (int64_t)g.TP * g.J;
+        t.stash_layer_stride = g.stash_layer_stride;
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
         // clusters of kTcCluster CTAs: even grid, never more clusters than tile pairs
         const int64_t pairs = (g.tc_tiles + tde::kTcCluster - 1) / tde::kTcCluster;
@@ -734,7 +741,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         t.wct = ws + g.o_wct; t.w_out = ws + g.o_wo;
         t.seeds = seeds; t.ld_seeds = ld_seeds; t.stash = stash;
         t.hbar = ws + g.o_hbar; t.zst = ws + g.o_zst;
-        t.stash_layer_stride = g.n_tiles * g.W * (int64_t)g.TP * g.J;
+        t.stash_layer_stride = g.stash_layer_stride;
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
         t.gpart = ws + g.o_gpart; t.gp_stride = g.gp_stride;
         t.gp_off_b_in = g.g_b_in; t.gp_off_b_hidden = g.g_bh; t.gp_off_w_out = g.g_wo; t.gp_off_b_out = g.g_bo;
