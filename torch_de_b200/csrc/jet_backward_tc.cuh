@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
     uint64_t* act_ready = empty + kMaxStages;
-    uint64_t* acc_ready = act_ready + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+    uint64_t* acc_ready = act_ready + 2;     // [neuron block]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
     unsigned char* zhi = smem_raw + 1024;
     constexpr uint32_t z_plane_c = (uint32_t)(W / 32) * ATOMK;
     const uint32_t z_plane = z_plane_c;
@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kTcCluster);
         }
-        mbar_init(act_ready, n_epi_warps);
-        mbar_init(acc_ready, 1);
+        for (int b = 0; b < MB; ++b) {
+            mbar_init(&act_ready[b], 4);     // the four epilogue warps of neuron block b
+            mbar_init(&acc_ready[b], 1);
+        }
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -129,46 +131,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
             const uint64_t b_hi0 = umma_desc_sw128(smem_u32(zhi), 1024);
             const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
             const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
-            const uint32_t stage_step = chunk_bytes >> 4, blk_step = 4096u >> 4;
-            constexpr int n_acc = kAccSets;
+            const uint32_t stage_step = chunk_bytes >> 4;
             int s = 0;
             uint32_t ph = 0, act_ph = 0;
-            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
-                for (int l = p.L - 1; l >= 1; --l) {
-                    mbar_wait(act_ready, act_ph);   // Hbar_l planes written, accumulators drained
-                    act_ph ^= 1;
-                    tc_fence_after();
-                    for (int ks = 0; ks < n_ks; ++ks) {
-                        mbar_wait(&full[s], ph);
-                        tc_fence_after();
-                        if (leader) {
-                            const uint32_t koff = ((uint32_t)(ks >> 2) * ATOMK + (uint32_t)(ks & 3) * 32u) >> 4;
-                            const uint64_t b_hi = b_hi0 + (uint64_t)koff;
-                            const uint64_t b_lo = b_lo0 + (uint64_t)koff;
-                            const uint64_t a_stage = a0 + (uint64_t)(s * stage_step);
-                            const uint32_t main_set = n_acc == 3 ? (uint32_t)(1 + (ks & 1)) : (n_acc == 2 ? 1u : 0u);
-                            const uint32_t acc_main = n_acc == 3 ? (uint32_t)(ks >= 2) : (n_acc == 2 ? (uint32_t)(ks > 0) : 1u);
-                            for (int mb = 0; mb < MB; ++mb) {
-                                const uint64_t a_hi = a_stage + (uint64_t)(mb * blk_step);
-                                const uint64_t a_lo = a_stage + (uint64_t)((MB + mb) * blk_step);
-                                const uint32_t d_small = tmem_base + (uint32_t)(mb * N);
-                                const uint32_t d_main = tmem_base + (uint32_t)((main_set * MB + mb) * N);
-                                umma_tf32(d_small, a_lo, b_hi, idesc, ks > 0);
-                                umma_tf32(d_small, a_hi, b_lo, idesc, 1);
-                                umma_tf32(d_main, a_hi, b_hi, idesc, acc_main);
-                            }
-                            umma_commit_mc(&empty[s], (uint16_t)((1u << kTcCluster) - 1));
-                        }
-                        __syncwarp();
-                        if (++s == n_stages) {
-                            s = 0;
-                            ph ^= 1;
-                        }
-                    }
-                    if (leader) umma_commit(acc_ready);
-                    __syncwarp();
-                }
-            }
+            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step)
+                for (int l = p.L - 1; l >= 1; --l)
+                    tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, idesc, a0, b_hi0, b_lo0, stage_step, full, empty, act_ready, acc_ready,
+                                                    n_stages, n_ks, s, ph, act_ph);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
@@ -226,19 +195,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                     uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
 #pragma unroll
                     for (int j = 0; j < 8; ++j) zaddr[j] = smem_u32(zhi) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u;
-                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && n == 0 && tile == 0 && l == 3;
-                    if (stamp) p.dbg_buf[0] = clock64();
+                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && pair == first_pair + 3 * pair_step && l >= 3 && l <= 5;
+                    long long* const dst = p.dbg_buf + 16 + ((5 - l) * 2 + mb) * 4;   // steady-state tile, both neuron blocks
+                    if (stamp) dst[0] = clock64();
                     float st_next[GC];
 #pragma unroll
                     for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)i * W);
                     uint32_t taddr = 0;
                     if (!last) {
-                        mbar_wait(acc_ready, acc_ph);
+                        mbar_wait(&acc_ready[mb], acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
                         taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
                     }
-                    if (stamp) p.dbg_buf[1] = clock64();
+                    if (stamp) dst[1] = clock64();
                     float db = 0.0f;
                     float dwo[TDE_MAX_OUT], dw_in[TDE_MAX_IN];
 #pragma unroll
@@ -344,13 +314,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
 #pragma unroll
                         for (int j = 0; j < 8; ++j) zaddr[j] += (uint32_t)(J * 1024);
                     }
-                    if (stamp) p.dbg_buf[3] = clock64();
+                    if (stamp) dst[2] = clock64();
                     if constexpr (KIND >= 1) {
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(act_ready);
-                        if (stamp) p.dbg_buf[4] = clock64();
+                        if (lane == 0) mbar_arrive(&act_ready[mb]);
+                        if (stamp) dst[3] = clock64();
                         slab_add(gp + p.gp_off_b_hidden + (size_t)(l - 1) * W + n, db, first);
                     } else {
                         slab_add(gp + p.gp_off_b_in + n, db, first);

@@ -175,6 +175,92 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
         tmem_ld_piece<1>(taddr, v);
     }
 }
+// One layer's GEMM, issued by the converged MMA warp (one elected lane issues, the whole warp runs the control flow: a
+// tcgen05.mma inside divergent code is wrapped by the compiler in an ELECT/branch loop of ~100 cycles each).
+//
+// The tensor core rounds its FP32 accumulator toward zero after every MMA: that bias, not the TF32 split, limits accuracy.
+// The 2^-11-sized cross terms get their own accumulator set and the main term alternates over two sets; the epilogue adds
+// them in FP32 (RN).
+//
+// W = 256 (MB = 2): the layer is issued as four quarters (neuron block mb, input half kh) in the order
+//   (0,0) (1,0) (0,1) (1,1), and each neuron block has its own act_ready / acc_ready barrier pair.  Quarter (0,0) needs only
+// the new activations of neurons 0..127 and the drained accumulators of block 0, so it runs while the epilogue warps of
+// block 1 still work on the previous layer; block 0's accumulators are complete after the third quarter, so its epilogue
+// runs under the fourth.  The weight image is packed in exactly this order (one 16 KB chunk = one block, two k-steps).
+template <int MB, int N, int kAccSets>
+__device__ __forceinline__ void tc_issue_layer(const bool leader, const uint32_t tmem_base, const uint32_t idesc, const uint64_t a0,
+                                               const uint64_t b_hi0, const uint64_t b_lo0, const uint32_t stage_step, uint64_t* full,
+                                               uint64_t* empty, uint64_t* act_ready, uint64_t* acc_ready, const int n_stages, const int n_ks,
+                                               int& s, uint32_t& ph, uint32_t& act_ph) {
+    constexpr uint32_t ATOMK = (N / 8) * 1024;
+    auto kstep = [&](const int ks, const int mb, const uint64_t a_hi, const uint64_t a_lo) {
+        // k-step ks: atom ks/4, then 32 B (8 tf32) per step inside the 128 B swizzled row
+        const uint32_t koff = ((uint32_t)(ks >> 2) * ATOMK + (uint32_t)(ks & 3) * 32u) >> 4;
+        const uint64_t b_hi = b_hi0 + (uint64_t)koff;
+        const uint64_t b_lo = b_lo0 + (uint64_t)koff;
+        const uint32_t main_set = kAccSets == 3 ? (uint32_t)(1 + (ks & 1)) : (kAccSets == 2 ? 1u : 0u);
+        const uint32_t acc_main = kAccSets == 3 ? (uint32_t)(ks >= 2) : (kAccSets == 2 ? (uint32_t)(ks > 0) : 1u);
+        const uint32_t d_small = tmem_base + (uint32_t)(mb * N);
+        const uint32_t d_main = tmem_base + (uint32_t)((main_set * MB + mb) * N);
+        umma_tf32(d_small, a_lo, b_hi, idesc, ks > 0);
+        umma_tf32(d_small, a_hi, b_lo, idesc, 1);
+        umma_tf32(d_main, a_hi, b_hi, idesc, acc_main);
+    };
+    auto advance = [&]() {
+        if (++s == n_stages) {
+            s = 0;
+            ph ^= 1;
+        }
+    };
+    if constexpr (MB == 1) {
+        mbar_wait(&act_ready[0], act_ph);   // planes of the previous layer are in smem, TMEM accumulators are drained
+        tc_fence_after();
+        for (int ks = 0; ks < n_ks; ++ks) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (leader) {
+                const uint64_t a_stage = a0 + (uint64_t)(s * stage_step);
+                kstep(ks, 0, a_stage, a_stage + (uint64_t)(4096u >> 4));
+                umma_commit_mc(&empty[s], (uint16_t)((1u << kTcCluster) - 1));   // stage is free in BOTH CTAs' view
+            }
+            __syncwarp();
+            advance();
+        }
+        if (leader) umma_commit(&acc_ready[0]);
+        __syncwarp();
+    } else {
+        const int ks_half = n_ks / 2;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const int mb = q & 1, kh = q >> 1;
+            if (q < 2) {
+                mbar_wait(&act_ready[q], act_ph);
+                tc_fence_after();
+            }
+            for (int cc = 0; cc < ks_half / 2; ++cc) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t a_stage = a0 + (uint64_t)(s * stage_step);
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        const uint64_t a_hi = a_stage + (uint64_t)(s2 * (8192 >> 4));
+                        kstep(kh * ks_half + cc * 2 + s2, mb, a_hi, a_hi + (uint64_t)(4096u >> 4));
+                    }
+                    umma_commit_mc(&empty[s], (uint16_t)((1u << kTcCluster) - 1));
+                }
+                __syncwarp();
+                advance();
+            }
+            if (q >= 2) {
+                if (leader) umma_commit(&acc_ready[q - 2]);
+                __syncwarp();
+            }
+        }
+    }
+    act_ph ^= 1;
+}
+
 constexpr int kTcGroup = 4;        // points handled per unrolled epilogue step (16 points = 4 steps)
 // accumulator sets that fit the 512 TMEM columns (3: cross terms | main even k-steps | main odd k-steps)
 __host__ __device__ constexpr int tc_acc_sets(int mb, int n) { return 512 / (mb * n) >= 3 ? 3 : 512 / (mb * n); }
@@ -197,8 +283,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
     uint64_t* act_ready = empty + kMaxStages;
-    uint64_t* acc_ready = act_ready + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+    uint64_t* acc_ready = act_ready + 2;     // [neuron block]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
     unsigned char* zhi = smem_raw + 1024;
     constexpr uint32_t z_plane_c = (uint32_t)(W / 32) * ATOMK;
     const uint32_t z_plane = z_plane_c;
@@ -219,8 +305,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], kTcCluster);   // one tcgen05.commit arrival from the MMA issuer of every CTA in the cluster
         }
-        mbar_init(act_ready, n_epi_warps);
-        mbar_init(acc_ready, 1);
+        for (int b = 0; b < MB; ++b) {
+            mbar_init(&act_ready[b], 4);     // the four epilogue warps of neuron block b
+            mbar_init(&acc_ready[b], 1);
+        }
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -249,7 +337,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                 for (int l = 1; l < p.L; ++l) {
                     const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wc) + (size_t)(l - 1) * n_ks * chunk_bytes;
                     for (int ks = 0; ks < n_ks; ++ks) {
-                        if (p.dbg & 1) continue;
                         mbar_wait(&empty[s], ph ^ 1);   // both CTAs have finished reading this stage
                         mbar_expect_tx(&full[s], chunk_bytes);      // my part + the peer's part will land here
                         bulk_g2s_mc(wst + (size_t)s * chunk_bytes + crank * part, src + (size_t)ks * chunk_bytes + crank * part, part,
@@ -270,8 +357,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
             const uint64_t b_hi0 = umma_desc_sw128(smem_u32(zhi), 1024);
             const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
             const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
-            const uint32_t stage_step = chunk_bytes >> 4, blk_step = 4096u >> 4;
-            constexpr int n_acc = kAccSets;
+            const uint32_t stage_step = chunk_bytes >> 4;
             int s = 0;
             uint32_t ph = 0, act_ph = 0;
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
@@ -279,43 +365,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                 for (int l = 1; l < p.L; ++l) {
                     const bool mstamp = p.dbg_buf && blockIdx.x == 0 && tile == 0 && l == 2 && lane == 0;
                     if (mstamp) p.dbg_buf[8] = clock64();
-                    mbar_wait(act_ready, act_ph);   // Z planes of layer l-1 are in smem, TMEM accumulators are free
-                    act_ph ^= 1;
-                    tc_fence_after();
-                    if (mstamp) p.dbg_buf[9] = clock64();
-                    for (int ks = 0; ks < n_ks; ++ks) {
-                        if (!(p.dbg & 1)) mbar_wait(&full[s], ph);
-                        tc_fence_after();
-                        if (leader && !(p.dbg & 2)) {
-                            // k-step ks: atom ks/4, then 32 B (8 tf32) per step inside the 128 B swizzled row
-                            const uint32_t koff = ((uint32_t)(ks >> 2) * ATOMK + (uint32_t)(ks & 3) * 32u) >> 4;
-                            const uint64_t b_hi = b_hi0 + (uint64_t)koff;
-                            const uint64_t b_lo = b_lo0 + (uint64_t)koff;
-                            const uint64_t a_stage = a0 + (uint64_t)(s * stage_step);
-                            // The tensor core rounds its FP32 accumulator toward zero after every MMA: that bias, not the
-                            // TF32 split, limits accuracy.  Keep the 2^-11-sized cross terms in their own accumulator and
-                            // alternate the main term over two accumulators; the epilogue adds them in FP32 (RN).
-                            const uint32_t main_set = n_acc == 3 ? (uint32_t)(1 + (ks & 1)) : (n_acc == 2 ? 1u : 0u);
-                            const uint32_t acc_main = n_acc == 3 ? (uint32_t)(ks >= 2) : (n_acc == 2 ? (uint32_t)(ks > 0) : 1u);
-                            for (int mb = 0; mb < MB; ++mb) {
-                                const uint64_t a_hi = a_stage + (uint64_t)(mb * blk_step);
-                                const uint64_t a_lo = a_stage + (uint64_t)((MB + mb) * blk_step);
-                                const uint32_t d_small = tmem_base + (uint32_t)(mb * N);
-                                const uint32_t d_main = tmem_base + (uint32_t)((main_set * MB + mb) * N);
-                                umma_tf32(d_small, a_lo, b_hi, idesc, ks > 0);
-                                umma_tf32(d_small, a_hi, b_lo, idesc, 1);
-                                umma_tf32(d_main, a_hi, b_hi, idesc, acc_main);
-                            }
-                            umma_commit_mc(&empty[s], (uint16_t)((1u << kTcCluster) - 1));   // stage is free in BOTH CTAs' view
-                        }
-                        __syncwarp();
-                        if (++s == n_stages) {
-                            s = 0;
-                            ph ^= 1;
-                        }
-                    }
-                    if (leader) umma_commit(acc_ready);  // accumulators of layer l complete
-                    __syncwarp();
+                    tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, idesc, a0, b_hi0, b_lo0, stage_step, full, empty, act_ready, acc_ready,
+                                                    n_stages, n_ks, s, ph, act_ph);
                     if (mstamp) p.dbg_buf[10] = clock64();
                 }
             }
@@ -363,6 +414,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                     float wrow[TDE_MAX_IN], wf[NF > 0 ? NF : 1];
                     float bn;
                     uint32_t taddr = 0;
+                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && pair == first_pair + 3 * pair_step && l >= 2 && l <= 4;
+                    long long* const dst = p.dbg_buf + 16 + ((l - 2) * 2 + mb) * 4;   // steady-state tile, both neuron blocks
+                    if (stamp) dst[0] = clock64();
                     if constexpr (kFirst) {
 #pragma unroll
                         for (int i = 0; i < TDE_MAX_IN; ++i) wrow[i] = i < p.d_in ? __ldg(p.w_in + n * p.d_in + i) : 0.0f;
@@ -371,12 +425,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                         for (int a = 0; a < NF; ++a) wf[a] = __ldg(p.w_in + n * p.d_in + p.first_in[a]);
                     } else {
                         bn = __ldg(p.b_hidden + (size_t)(l - 1) * W + n);
-                        mbar_wait(acc_ready, acc_ph);
+                        mbar_wait(&acc_ready[mb], acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
                         taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
                     }
                     const float* xs_h = xs;
+                    if (stamp) dst[1] = clock64();
 #pragma unroll 1
                     for (int half = 0; half < 2; ++half) {
                         if constexpr (kStash) asm volatile("" : "+l"(srow_h));
@@ -436,13 +491,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
 #pragma unroll
                         for (int j = 0; j < 8; ++j) zaddr[j] += (uint32_t)(J * 1024);   // 8 points = J column groups of 8
                     }
+                    if (stamp) dst[2] = clock64();
                     if (l < p.L - 1) {
                         // publish: smem writes -> async proxy, TMEM reads retired, then one arrive per warp
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(act_ready);
+                        if (lane == 0) mbar_arrive(&act_ready[mb]);
                     }
+                    if (stamp) dst[3] = clock64();
                 };
                 if (stash_row) {
                     layer_body(std::true_type{}, std::true_type{}, 0);

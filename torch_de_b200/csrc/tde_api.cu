@@ -361,12 +361,23 @@ __global__ void pack_tc_weights_kernel(const __grid_constant__ PackArgs a, float
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int l = (int)(i / per_layer) + 1;
         int64_t r = i % per_layer;
-        const int ks = (int)(r / chunk);
+        const int ci = (int)(r / chunk);
         int c = (int)(r % chunk);
-        const int hl = c / (MB * 1024); c %= MB * 1024;
-        const int mb = c / 1024;        c %= 1024;
-        const int kg = c / 512;         c %= 512;
-        const int rg = c / 32;          c %= 32;
+        int hl, mb, ks, kg;
+        if (MB == 1) {          // one chunk per k-step: [hi|lo][k group 2][16 row groups][8][4]
+            ks = ci;
+            mb = 0;
+            hl = c / 1024;      c %= 1024;
+        } else {                // MB == 2: chunks follow the issue order of tc_issue_layer: quarter (mb, k half), two k-steps each
+            const int per_q = W / 32;          // chunks per quarter
+            const int q = ci / per_q, cc = ci % per_q;
+            mb = q & 1;
+            const int s2 = c / 2048; c %= 2048;
+            ks = (q >> 1) * (W / 16) + cc * 2 + s2;
+            hl = c / 1024;      c %= 1024;
+        }
+        kg = c / 512;           c %= 512;
+        const int rg = c / 32;  c %= 32;
         const int rr = c / 4, kk = c % 4;
         const int n = mb * 128 + rg * 8 + rr, k = ks * 8 + kg * 4 + kk;
         float v = 0.0f;
@@ -686,7 +697,7 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
         { const char* d = getenv("TDE_TC_DBG"); t.dbg = d ? atoi(d) : 0; }
         static long long* dbg_buf = nullptr;
         if (t.dbg & 4) {
-            if (!dbg_buf) { cudaMalloc(&dbg_buf, 16 * sizeof(long long)); cudaMemset(dbg_buf, 0, 16 * sizeof(long long)); }
+            if (!dbg_buf) { cudaMalloc(&dbg_buf, 64 * sizeof(long long)); cudaMemset(dbg_buf, 0, 64 * sizeof(long long)); }
             t.dbg_buf = dbg_buf;
         }
         for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
@@ -703,11 +714,16 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
             TDE_CUDA(g.disp->fwd_tc(t, grid, g.tc_smem, st));
         }
         if (t.dbg & 4) {
-            long long h[16];
+            long long h[64];
             cudaStreamSynchronize(st);
             cudaMemcpy(h, dbg_buf, sizeof h, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[tc dbg] epi: wait_acc %lld  tmem_ld %lld  math+sts %lld  stash %lld  publish %lld | mma: wait_act %lld  issue+commit %lld | epi_start-to-mma_done %lld\n",
-                    h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[9] - h[8], h[10] - h[9], h[10] - h[0]);
+            // 4th tile of CTA 0, layers 2..4, neuron blocks 0/1: [body start, accumulators ready, body end, published], relative
+            for (int l = 0; l < 3; ++l)
+                for (int b = 0; b < 2; ++b) {
+                    const long long* d = h + 16 + (l * 2 + b) * 4;
+                    fprintf(stderr, "[tc dbg] fwd layer %d block %d: start %lld  acc_ready %lld  body_end %lld  published %lld\n", l + 2, b,
+                            d[0] - h[16], d[1] - h[16], d[2] - h[16], d[3] - h[16]);
+                }
         }
     } else {
         tde::JetParams p;
@@ -752,7 +768,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         static long long* bdbg = nullptr;
         const char* dbg_env = getenv("TDE_TC_DBG");
         if (dbg_env && (atoi(dbg_env) & 4)) {
-            if (!bdbg) { cudaMalloc(&bdbg, 16 * sizeof(long long)); cudaMemset(bdbg, 0, 16 * sizeof(long long)); }
+            if (!bdbg) { cudaMalloc(&bdbg, 64 * sizeof(long long)); cudaMemset(bdbg, 0, 64 * sizeof(long long)); }
             t.dbg_buf = bdbg;
         }
         {
@@ -760,11 +776,15 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
             TDE_CUDA(g.disp->bwd_tc(t, (int)g.grid_b1, g.tc_smem, st));
         }
         if (t.dbg_buf) {
-            long long h[16];
+            long long h[64];
             cudaStreamSynchronize(st);
             cudaMemcpy(h, bdbg, sizeof h, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[tc bwd dbg] stash_ld_issue+wait_acc %lld  tmem_ld %lld  adjoint+stores %lld  publish %lld\n", h[1] - h[0],
-                    h[2] - h[1], h[3] - h[2], h[4] - h[3]);
+            for (int l = 0; l < 3; ++l)
+                for (int b = 0; b < 2; ++b) {
+                    const long long* d = h + 16 + (l * 2 + b) * 4;
+                    fprintf(stderr, "[tc dbg] bwd layer %d block %d: start %lld  acc_ready %lld  body_end %lld  published %lld\n", 5 - l, b,
+                            d[0] - h[16], d[1] - h[16], d[2] - h[16], d[3] - h[16]);
+                }
         }
         {
             ScopedTimer timer(st, 2);
