@@ -35,6 +35,7 @@ struct TcBwdParams {
     int tiles_per_bw_tile;
     float* gpart;               // per-CTA slabs
     int64_t gp_stride, gp_off_b_in, gp_off_b_hidden, gp_off_w_out, gp_off_b_out;
+    int64_t gp_dup_lo, gp_dup_hi;   // offsets of the second copy of (w_in | b_in) and (b_hidden | w_out | b_out) inside a slab
     long long* dbg_buf;         // optional cycle stamps
 };
 
@@ -47,7 +48,7 @@ __device__ __forceinline__ void slab_add(float* dst, float v, bool first) {
 }
 
 template <int NF, int SMASK, int W>
-__global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __grid_constant__ TcBwdParams p) {
+__global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const __grid_constant__ TcBwdParams p) {
     using S = JetSpecT<NF, SMASK>;
     constexpr int J = S::J;
     constexpr int N = kTcPoints * J;
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
     float* seeds_s = xs + kTcPoints * p.d_in;         // [J*n_out][16]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_epi_warps = 4 * MB;
-    const int n_epi = 128 * MB;
+    constexpr int n_epi_warps = 8 * MB;
+    constexpr int n_epi = 256 * MB;
     const int n_ks = W / kTcKC;
 
     if (tid == 0) {
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
             mbar_init(&empty[s], kTcCluster);
         }
         for (int b = 0; b < MB; ++b) {
-            mbar_init(&act_ready[b], 4);     // the four epilogue warps of neuron block b
+            mbar_init(&act_ready[b], 8);     // the eight epilogue warps of neuron block b
             mbar_init(&acc_ready[b], 1);
         }
         mbar_fence_init();
@@ -140,11 +141,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                                                     n_stages, n_ks, s, ph, act_ph);
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tc_epi_regs(W)));
         const int e = warp - 4;
         if (e < n_epi_warps) {
             const int quarter = warp & 3;
-            const int mb = e >> 2;
+            const int mb = (e >> 2) % MB;            // neuron block
+            const int ph = (e >> 2) / MB;            // point half: this thread handles points 8*ph .. 8*ph+7 of every tile
             const int n = mb * 128 + quarter * 32 + lane;   // the neuron this thread owns (in every layer)
             const int et = e * 32 + lane;
             auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory"); };
@@ -152,7 +154,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
             for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
             const uint32_t zrow = (uint32_t)(n >> 5) * ATOMK + (uint32_t)(n & 3) * 4u;
             const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;
+            // the two threads of a neuron (one per point half) add into separate copies of the small gradient sections
             float* gp = p.gpart + (size_t)blockIdx.x * p.gp_stride;
+            float* gp_lo = gp + (ph ? p.gp_dup_lo : 0);      // w_in | b_in
+            float* gp_hi = gp + (ph ? p.gp_dup_hi : 0);      // b_hidden | w_out | b_out
             uint32_t acc_ph = 0;
 
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                     seeds_s[i] = gpt < p.B ? p.seeds[(size_t)r * p.ld_seeds + gpt] : 0.0f;
                 }
                 epi_sync();
-                const size_t row0 = (size_t)tile * N * W + n;     // [layer][tile][jet column][neuron]
+                const size_t row0 = ((size_t)tile * N + (size_t)ph * (8 * J)) * W + n;     // [layer][tile][jet column][neuron]
 
                 // Epilogue as 2 x (2 steps of 4 points): 8 points are unrolled so every shared/global offset is an immediate (a
                 // 16-point unroll is >200 KB of code and instruction-cache bound).  The stash values of the NEXT 4-point step
@@ -194,8 +199,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                     float* zrow_h = p.zst + loff;
                     uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) zaddr[j] = smem_u32(zhi) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u;
-                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && pair == first_pair + 3 * pair_step && l >= 3 && l <= 5;
+                    for (int j = 0; j < 8; ++j)
+                        zaddr[j] = smem_u32(zhi) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph * (uint32_t)(J * 1024);
+                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && ph == 0 && pair == first_pair + 3 * pair_step && l >= 3 && l <= 5;
                     long long* const dst = p.dbg_buf + 16 + ((5 - l) * 2 + mb) * 4;   // steady-state tile, both neuron blocks
                     if (stamp) dst[0] = clock64();
                     float st_next[GC];
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                         mbar_wait(&acc_ready[mb], acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
-                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
+                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N + ph * 2 * GC);
                     }
                     if (stamp) dst[1] = clock64();
                     float db = 0.0f;
@@ -215,10 +221,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                     for (int o = 0; o < TDE_MAX_OUT; ++o) dwo[o] = 0.0f;
 #pragma unroll
                     for (int i = 0; i < TDE_MAX_IN; ++i) dw_in[i] = 0.0f;
-                    const float* xs_h = xs;
-                    const float* seeds_h = seeds_s;
-#pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
+                    const float* xs_h = xs + ph * 8 * p.d_in;
+                    const float* seeds_h = seeds_s + ph * 8;
+                    {
                         asm volatile("" : "+l"(srow_h), "+l"(hrow_h), "+l"(zrow_h));
 #pragma unroll
                         for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
@@ -230,9 +235,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                             if (g2 == 0) {
 #pragma unroll
                                 for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)(GC + i) * W);
-                            } else if (half == 0) {
-#pragma unroll
-                                for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)(2 * GC + i) * W);
                             }
                             if (!last) {
                                 float cur[kAccSets][GC];
@@ -305,14 +307,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                                 }
                             }
                         }
-                        srow_h += (size_t)(8 * J) * W;
-                        hrow_h += (size_t)(8 * J) * W;
-                        zrow_h += (size_t)(8 * J) * W;
-                        taddr += 2 * GC;
-                        xs_h += 8 * p.d_in;
-                        seeds_h += 8;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) zaddr[j] += (uint32_t)(J * 1024);
                     }
                     if (stamp) dst[2] = clock64();
                     if constexpr (KIND >= 1) {
@@ -321,17 +315,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_backward_tc_kernel(const __
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&act_ready[mb]);
                         if (stamp) dst[3] = clock64();
-                        slab_add(gp + p.gp_off_b_hidden + (size_t)(l - 1) * W + n, db, first);
+                        slab_add(gp_hi + p.gp_off_b_hidden + (size_t)(l - 1) * W + n, db, first);
                     } else {
-                        slab_add(gp + p.gp_off_b_in + n, db, first);
+                        slab_add(gp_lo + p.gp_off_b_in + n, db, first);
 #pragma unroll
                         for (int i = 0; i < TDE_MAX_IN; ++i)
-                            if (i < p.d_in) slab_add(gp + (size_t)n * p.d_in + i, dw_in[i], first);
+                            if (i < p.d_in) slab_add(gp_lo + (size_t)n * p.d_in + i, dw_in[i], first);
                     }
                     if (last) {
 #pragma unroll
                         for (int o = 0; o < TDE_MAX_OUT; ++o)
-                            if (o < p.n_out) slab_add(gp + p.gp_off_w_out + (size_t)o * W + n, dwo[o], first);
+                            if (o < p.n_out) slab_add(gp_hi + p.gp_off_w_out + (size_t)o * W + n, dwo[o], first);
                     }
                 };
                 layer_body(std::integral_constant<int, 2>{}, p.L - 1);

@@ -18,7 +18,12 @@ namespace tde {
 
 constexpr int kTcPoints = 16;      // points per tile
 constexpr int kTcKC = 8;           // k rows per weight chunk (= one tf32 MMA K step)
-constexpr int kTcThreads = 384;    // 4 control warps + 8 epilogue warps
+// 4 control warps + 8 epilogue warps per 128-neuron block: a warp may only read the TMEM lanes 32*(warp%4)..+31, so every
+// lane quarter gets two warps, one per half of the tile's 16 points
+__host__ __device__ constexpr int tc_threads(int W) { return 128 + 256 * (W / 128); }
+// registers per epilogue thread after setmaxnreg (control warps keep 24).  The pool is what the CTA was launched with:
+// 640 threads x 96 registers, so (61440 - 128*24) / 512 = 114 -> 112; asking for more blocks forever
+__host__ __device__ constexpr int tc_epi_regs(int W) { return W == 256 ? 112 : 232; }
 constexpr int kTcCluster = 2;      // CTAs per cluster: each loads 1/2 of every weight chunk and multicasts it to both
 
 struct TcParams {
@@ -267,7 +272,7 @@ __host__ __device__ constexpr int tc_acc_sets(int mb, int n) { return 512 / (mb 
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 template <int NF, int SMASK, int W>
-__global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const __grid_constant__ TcParams p) {
     using S = JetSpecT<NF, SMASK>;
     constexpr int J = S::J;
     constexpr int N = kTcPoints * J;             // jet columns per tile (multiple of 16)
@@ -296,8 +301,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
     float* ybuf = xs + kTcPoints * p.d_in;       // [J*n_out][16]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_epi_warps = 4 * MB;
-    const int n_epi = 128 * MB;
+    constexpr int n_epi_warps = 8 * MB;
+    constexpr int n_epi = 256 * MB;
     const int n_ks = W / kTcKC;
 
     if (tid == 0) {
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
             mbar_init(&empty[s], kTcCluster);   // one tcgen05.commit arrival from the MMA issuer of every CTA in the cluster
         }
         for (int b = 0; b < MB; ++b) {
-            mbar_init(&act_ready[b], 4);     // the four epilogue warps of neuron block b
+            mbar_init(&act_ready[b], 8);     // the eight epilogue warps of neuron block b
             mbar_init(&acc_ready[b], 1);
         }
         mbar_fence_init();
@@ -372,11 +377,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
-        const int e = warp - 4;                      // epilogue warp 0..7
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tc_epi_regs(W)));
+        const int e = warp - 4;                      // epilogue warp
         if (e < n_epi_warps) {
             const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-            const int mb = e >> 2;
+            const int mb = (e >> 2) % MB;            // neuron block
+            const int ph = (e >> 2) / MB;            // point half: this thread handles points 8*ph .. 8*ph+7 of every tile
             const int n = mb * 128 + quarter * 32 + lane;   // the neuron this thread owns
             const int et = e * 32 + lane;            // 0..n_epi-1 dense index for strided loops
             auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory"); };
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                 epi_sync();
                 // [layer][tile][jet column][neuron]: this thread's neuron, first column of the tile.  A padding tile (the second
                 // tile of the last pair when the tile count is odd) has stash rows of its own and x = 0.
-                float* const stash_row = p.stash ? p.stash + (size_t)tile * N * W + n : nullptr;
+                float* const stash_row = p.stash ? p.stash + ((size_t)tile * N + (size_t)ph * (8 * J)) * W + n : nullptr;
 
                 // Per layer the epilogue walks the 16 points as 2 x (2 steps of 4 points): 8 points are unrolled so every
                 // shared/global offset is an immediate (a 16-point unroll is >80 KB of code and instruction-cache bound).
@@ -410,11 +416,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                     float* srow_h = kStash ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
                     uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) zaddr[j] = smem_u32(zhi) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u;
+                    for (int j = 0; j < 8; ++j)
+                        zaddr[j] = smem_u32(zhi) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph * (uint32_t)(J * 1024);
                     float wrow[TDE_MAX_IN], wf[NF > 0 ? NF : 1];
                     float bn;
                     uint32_t taddr = 0;
-                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && pair == first_pair + 3 * pair_step && l >= 2 && l <= 4;
+                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && ph == 0 && pair == first_pair + 3 * pair_step && l >= 2 && l <= 4;
                     long long* const dst = p.dbg_buf + 16 + ((l - 2) * 2 + mb) * 4;   // steady-state tile, both neuron blocks
                     if (stamp) dst[0] = clock64();
                     if constexpr (kFirst) {
@@ -428,12 +435,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                         mbar_wait(&acc_ready[mb], acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
-                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N);
+                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N + ph * 2 * GC);
                     }
-                    const float* xs_h = xs;
+                    const float* xs_h = xs + ph * 8 * p.d_in;
                     if (stamp) dst[1] = clock64();
-#pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
+                    {
                         if constexpr (kStash) asm volatile("" : "+l"(srow_h));
 #pragma unroll
                         for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
@@ -485,11 +491,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) jet_forward_tc_kernel(const __g
                                 }
                             }
                         }
-                        if constexpr (kStash) srow_h += (size_t)(8 * J) * W;
-                        taddr += 2 * GC;
-                        xs_h += 8 * p.d_in;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) zaddr[j] += (uint32_t)(J * 1024);   // 8 points = J column groups of 8
                     }
                     if (stamp) dst[2] = clock64();
                     if (l < p.L - 1) {

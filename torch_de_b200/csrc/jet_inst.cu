@@ -32,7 +32,7 @@ cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p,
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kTcThreads);
+    cfg.blockDim = dim3(tc_threads(p.W));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -51,7 +51,7 @@ cudaError_t TDE_CAT(launch_backward_tc_, TDE_NF, _, TDE_SMASK)(const TcBwdParams
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kTcThreads);
+    cfg.blockDim = dim3(tc_threads(p.W));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

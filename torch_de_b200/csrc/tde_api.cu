@@ -100,6 +100,7 @@ struct Geometry {
     int64_t o_gpart;
     int64_t workspace_floats;
     int64_t stash_floats, stash_layer_stride;
+    int64_t g_dup_lo, g_dup_hi;
     int64_t n_params;
     const Dispatch* disp;
 };
@@ -266,6 +267,15 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.g_bh = q;     q += (int64_t)(L - 1) * g.W;
     g.g_wo = q;     q = align_up(q + (int64_t)g.n_out * g.W, 4);
     g.g_bo = q;     q = align_up(q + g.n_out, 4);
+    g.g_dup_lo = g.g_dup_hi = 0;
+    if (g.use_tc_bwd) {
+        // the tcgen05 reverse sweep has two threads per neuron (one per half of a tile's points): the second one adds into
+        // its own copy of (w_in | b_in) and (b_hidden | w_out); the reduction sums both copies in a fixed order
+        const int64_t small_end = q;
+        g.g_dup_lo = q;                                  // copy of [0, g_hidden)
+        g.g_dup_hi = q + g.g_hidden - g.g_bh;            // copy of [g_bh, small_end) starts at q + g_hidden
+        q = align_up(q + g.g_hidden + (small_end - g.g_bh), 4);
+    }
     g.gp_stride = q;
     g.o_gpart = g.packed_floats;
     // The tcgen05 kernels walk 16-point tiles in cluster pairs: when the tile count is odd the last pair's second tile is
@@ -434,6 +444,7 @@ struct ReduceArgs {
     int n_layers, W, width, d_in, n_out, rsplit, n_active, n_active_hidden;
     int64_t n_params, gp_stride;
     int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo;
+    int64_t dup_lo, dup_hi;      // second copy of the small sections (tcgen05 reverse sweep), 0 if absent
     float scale;
 };
 
@@ -479,9 +490,12 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
     }
     float s = 0.0f;
     const int n_slabs = splits > 1 || src >= a.g_hidden && src < a.g_bh ? a.n_active_hidden : a.n_active;
+    int64_t dup = 0;
+    if (a.dup_lo) dup = src < a.g_hidden ? a.dup_lo : (src >= a.g_bh && src < a.g_bo ? a.dup_hi : 0);
     for (int c = 0; c < n_slabs; ++c) {
         const float* slab = gpart + (int64_t)c * a.gp_stride + src;
         for (int q = 0; q < splits; ++q) s += slab[(int64_t)q * WW];
+        if (dup) s += slab[dup];
     }
     flat[i] += a.scale * s;
 }
@@ -761,6 +775,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
         t.gpart = ws + g.o_gpart; t.gp_stride = g.gp_stride;
         t.gp_off_b_in = g.g_b_in; t.gp_off_b_hidden = g.g_bh; t.gp_off_w_out = g.g_wo; t.gp_off_b_out = g.g_bo;
+        t.gp_dup_lo = g.g_dup_lo; t.gp_dup_hi = g.g_dup_hi;
         tde::TcDwParams d{};
         d.n_tiles = g.tc_tiles; d.L = g.L; d.W = g.W; d.MB = g.tc_mb; d.J = g.J;
         d.hbar = t.hbar; d.zst = t.zst; d.stash_layer_stride = t.stash_layer_stride; d.tiles_per_bw_tile = t.tiles_per_bw_tile;
@@ -813,6 +828,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
     r.n_layers = net->n_layers; r.W = g.W; r.width = g.width; r.d_in = g.d_in; r.n_out = g.n_out;
     r.rsplit = g.rsplit; r.n_active = n_active; r.n_active_hidden = n_active_hidden; r.n_params = g.n_params; r.gp_stride = g.gp_stride;
     r.g_b_in = g.g_b_in; r.g_hidden = g.g_hidden; r.g_bh = g.g_bh; r.g_wo = g.g_wo; r.g_bo = g.g_bo;
+    r.dup_lo = n_active_hidden ? g.g_dup_lo : 0; r.dup_hi = n_active_hidden ? g.g_dup_hi : 0;
     r.scale = grad_scale;
     const int threads = 256;
     reduce_grads_kernel<<<(int)((g.n_params + threads - 1) / threads), threads, 0, st>>>(r, ws + g.o_gpart, flat_grad);
