@@ -23,6 +23,7 @@ struct TcBwdParams {
     int64_t n_tiles;            // 16-point tiles
     int d_in, n_out, L, W, act, MB;
     int n_stages, n_acc, fourier_half;
+    int pair;                   // W = 256: use the CTA-pair kernel
     int first_in[TDE_MAX_FIRST];
     const float* wct;           // transposed-weight chunk images [(L-1)][W/8][chunk]
     const float* w_out;         // [n_out][W] packed
@@ -35,7 +36,7 @@ struct TcBwdParams {
     int tiles_per_bw_tile;
     float* gpart;               // per-CTA slabs
     int64_t gp_stride, gp_off_b_in, gp_off_b_hidden, gp_off_w_out, gp_off_b_out;
-    int64_t gp_dup_lo, gp_dup_hi;   // offsets of the second copy of (w_in | b_in) and (b_hidden | w_out | b_out) inside a slab
+    int64_t gp_dup_lo[4], gp_dup_hi[4];   // slab offsets of copy k of (w_in | b_in) and (b_hidden | w_out); [0] = 0
     long long* dbg_buf;         // optional cycle stamps
 };
 
@@ -60,8 +61,8 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
     constexpr int kAccSets = tc_acc_sets(MB, N);
     const int n_stages = p.n_stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* empty = full + kMaxStages;
-    uint64_t* act_ready = empty + kMaxStages;
+    uint64_t* empty = full + kTcMaxStages;
+    uint64_t* act_ready = empty + kTcMaxStages;
     uint64_t* acc_ready = act_ready + 2;     // [neuron block]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
     unsigned char* zhi = smem_raw + 1024;
@@ -156,8 +157,8 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
             const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;
             // the two threads of a neuron (one per point half) add into separate copies of the small gradient sections
             float* gp = p.gpart + (size_t)blockIdx.x * p.gp_stride;
-            float* gp_lo = gp + (ph ? p.gp_dup_lo : 0);      // w_in | b_in
-            float* gp_hi = gp + (ph ? p.gp_dup_hi : 0);      // b_hidden | w_out | b_out
+            float* gp_lo = gp + p.gp_dup_lo[ph];      // w_in | b_in
+            float* gp_hi = gp + p.gp_dup_hi[ph];      // b_hidden | w_out
             uint32_t acc_ph = 0;
 
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kDwThreads = 640;       // warp 1: MMA issuer, warps 4..11: Hbar loaders + flushers, warps 12..19: Z loaders (one thread per neuron)
 constexpr int kDwStages = 6;          // operand stages, one 8-column k-step each
+constexpr int kDwAhead = 5;           // register-buffered k-steps a loader thread keeps in flight
 constexpr int kDwFlushTiles = 8;      // accumulator is flushed to the slab after this many 16-point tiles
 
 struct TcDwParams {
@@ -471,18 +473,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                 const float* zsrc = p.zst + (size_t)(l - 1) * p.stash_layer_stride;
                 for (int64_t t0 = 0; t0 < my_tiles; t0 += kDwFlushTiles) {
                     const int64_t t1 = t0 + kDwFlushTiles < my_tiles ? t0 + kDwFlushTiles : my_tiles;
-                    // Loads run 3 stages ahead of the stores (ring of 4 register buffers): ~48 KB in flight per SM covers the
-                    // HBM latency at the rate the MMAs consume stages.
+                    // Loads run kDwAhead stages ahead of the stores (ring of kDwAhead + 1 register buffers): the bytes in flight
+                    // per SM (512 loader threads x kDwAhead x 32 B) have to cover the HBM latency at the rate the MMAs consume.
                     const int total = (int)(t1 - t0) * n_ks;
                     int64_t lt = t0;       // load cursor: tile, k-step
                     int lks = 0;
-                    float hv[4][8];
+                    float hv[kDwAhead + 1][8];
                     const float* src = which ? zsrc : hsrc;
                     auto issue_loads = [&](float (&h8)[8]) {
                         const int64_t tile = blockIdx.x + lt * gridDim.x;
-                        const int64_t bw_tile = tile / p.tiles_per_bw_tile;
-                        const int sub = (int)(tile - bw_tile * p.tiles_per_bw_tile);
-                        const size_t row0 = ((size_t)bw_tile * p.tiles_per_bw_tile * N + (size_t)sub * N + (size_t)lks * 8) * W + n;
+                        const size_t row0 = ((size_t)tile * N + (size_t)lks * 8) * W + n;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) h8[c] = __ldcs(src + row0 + (size_t)c * W);
                         if (++lks == n_ks) {
@@ -513,13 +513,13 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                         }
                     };
 #pragma unroll
-                    for (int b = 0; b < 3; ++b)
+                    for (int b = 0; b < kDwAhead; ++b)
                         if (b < total) issue_loads(hv[b]);
-                    for (int j = 0; j < total; j += 4) {
+                    for (int j = 0; j < total; j += kDwAhead + 1) {
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) {
+                        for (int b = 0; b < kDwAhead + 1; ++b) {
                             if (j + b < total) {
-                                if (j + b + 3 < total) issue_loads(hv[(b + 3) & 3]);
+                                if (j + b + kDwAhead < total) issue_loads(hv[(b + kDwAhead) % (kDwAhead + 1)]);
                                 store_stage(hv[b]);
                             }
                         }

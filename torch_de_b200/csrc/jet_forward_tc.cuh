@@ -18,13 +18,17 @@ namespace tde {
 
 constexpr int kTcPoints = 16;      // points per tile
 constexpr int kTcKC = 8;           // k rows per weight chunk (= one tf32 MMA K step)
+constexpr int kTcMaxStages = 8;   // weight stages of the tensor-core kernels (as many as shared memory allows)
 // 4 control warps + 8 epilogue warps per 128-neuron block: a warp may only read the TMEM lanes 32*(warp%4)..+31, so every
 // lane quarter gets two warps, one per half of the tile's 16 points
 __host__ __device__ constexpr int tc_threads(int W) { return 128 + 256 * (W / 128); }
 // registers per epilogue thread after setmaxnreg (control warps keep 24).  The pool is what the CTA was launched with:
 // 640 threads x 96 registers, so (61440 - 128*24) / 512 = 114 -> 112; asking for more blocks forever
 __host__ __device__ constexpr int tc_epi_regs(int W) { return W == 256 ? 112 : 232; }
-constexpr int kTcCluster = 2;      // CTAs per cluster: each loads 1/2 of every weight chunk and multicasts it to both
+#ifndef TDE_TC_CLUSTER
+#define TDE_TC_CLUSTER 2
+#endif
+constexpr int kTcCluster = TDE_TC_CLUSTER;      // CTAs per cluster: each loads 1/kTcCluster of every weight chunk and multicasts it to all
 
 struct TcParams {
     const float* x;
@@ -34,7 +38,8 @@ struct TcParams {
     int n_stages;
     int fourier_half;      // > 0: layer 0 is a Fourier embedding (sin half | cos half)
     long long* dbg_buf;    // optional cycle stamps (TDE_TC_DBG bit 2)
-    int dbg;               // bit0: skip weight streaming (timing experiment only)
+    int dbg;               // bit 2: cycle stamps; bit 3: pair kernel without weight streaming (timing experiment only)
+    int pair;              // W = 256: use the CTA-pair kernel
     int n_acc;             // TMEM accumulator sets: 3 = {small terms, main even k-steps, main odd k-steps}, 2, or 1
     int first_in[TDE_MAX_FIRST];
     const float* w_in;     // [W][d_in]
@@ -286,8 +291,8 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
     constexpr int kAccSets = tc_acc_sets(MB, N);
     const int n_stages = p.n_stages;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* empty = full + kMaxStages;
-    uint64_t* act_ready = empty + kMaxStages;
+    uint64_t* empty = full + kTcMaxStages;
+    uint64_t* act_ready = empty + kTcMaxStages;
     uint64_t* acc_ready = act_ready + 2;     // [neuron block]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
     unsigned char* zhi = smem_raw + 1024;

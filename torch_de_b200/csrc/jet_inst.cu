@@ -3,12 +3,25 @@
 #include "jet_backward.cuh"
 #include "jet_forward_tc.cuh"
 #include "jet_backward_tc.cuh"
+#include "jet_pair_tc.cuh"
 #include "jet_launch.h"
 
 #define TDE_CAT_(a, b, c, d) a##b##_##d
 #define TDE_CAT(a, b, c, d) TDE_CAT_(a, b, c, d)
 
 namespace tde {
+
+// CTA-pair kernels exist for jet specs with N = 32 J <= 256 only
+template <int NF, int SMASK, bool OK = (JetSpecT<NF, SMASK>::J <= 8)>
+struct PairKernels {
+    static void (*fwd())(TcParams) { return jet_forward_pair_kernel<NF, SMASK>; }
+    static void (*bwd())(TcBwdParams) { return jet_backward_pair_kernel<NF, SMASK>; }
+};
+template <int NF, int SMASK>
+struct PairKernels<NF, SMASK, false> {
+    static void (*fwd())(TcParams) { return nullptr; }
+    static void (*bwd())(TcBwdParams) { return nullptr; }
+};
 
 cudaError_t TDE_CAT(launch_forward_, TDE_NF, _, TDE_SMASK)(const JetParams& p, int grid, int smem, cudaStream_t st) {
     auto k = jet_forward_kernel<TDE_NF, TDE_SMASK>;
@@ -27,17 +40,24 @@ cudaError_t TDE_CAT(launch_backward_, TDE_NF, _, TDE_SMASK)(const JetParams& p, 
 }
 
 cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p, int grid, int smem, cudaStream_t st) {
-    auto k = p.W == 256 ? jet_forward_tc_kernel<TDE_NF, TDE_SMASK, 256> : jet_forward_tc_kernel<TDE_NF, TDE_SMASK, 128>;
+    void (*k)(TcParams) = p.W == 256 ? jet_forward_tc_kernel<TDE_NF, TDE_SMASK, 256> : jet_forward_tc_kernel<TDE_NF, TDE_SMASK, 128>;
+    int threads = tc_threads(p.W), cluster = kTcCluster;
+    if (p.pair) {
+        k = PairKernels<TDE_NF, TDE_SMASK>::fwd();
+        threads = kPairThreads;
+        cluster = kPairCluster;
+        if (!k) return cudaErrorInvalidValue;
+    }
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(tc_threads(p.W));
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kTcCluster;
+    attr[0].val.clusterDim.x = cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -46,22 +66,54 @@ cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p,
 }
 
 cudaError_t TDE_CAT(launch_backward_tc_, TDE_NF, _, TDE_SMASK)(const TcBwdParams& p, int grid, int smem, cudaStream_t st) {
-    auto k = p.W == 256 ? jet_backward_tc_kernel<TDE_NF, TDE_SMASK, 256> : jet_backward_tc_kernel<TDE_NF, TDE_SMASK, 128>;
+    void (*k)(TcBwdParams) = p.W == 256 ? jet_backward_tc_kernel<TDE_NF, TDE_SMASK, 256> : jet_backward_tc_kernel<TDE_NF, TDE_SMASK, 128>;
+    int threads = tc_threads(p.W), cluster = kTcCluster;
+    if (p.pair) {
+        k = PairKernels<TDE_NF, TDE_SMASK>::bwd();
+        threads = kPairThreads;
+        cluster = kPairCluster;
+        if (!k) return cudaErrorInvalidValue;
+    }
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(tc_threads(p.W));
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kTcCluster;
+    attr[0].val.clusterDim.x = cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k, p);
+}
+
+// how many clusters of the pair kernels can be resident at once (a cluster of 4 must fit inside one GPC, so it can be fewer
+// than SMs / 4); the persistent grid must not exceed it.  Returns 0 when the spec has no pair kernel, -1 on error.
+int TDE_CAT(pair_max_clusters_, TDE_NF, _, TDE_SMASK)(int smem) {
+    void (*kf)(TcParams) = PairKernels<TDE_NF, TDE_SMASK>::fwd();
+    void (*kb)(TcBwdParams) = PairKernels<TDE_NF, TDE_SMASK>::bwd();
+    if (!kf || !kb) return 0;
+    if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kPairCluster * 64);
+    cfg.blockDim = dim3(kPairThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kPairCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nf = 0, nb = 0;
+    if (cudaOccupancyMaxActiveClusters(&nf, kf, &cfg) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveClusters(&nb, kb, &cfg) != cudaSuccess) return -1;
+    return nf < nb ? nf : nb;
 }
 
 }  // namespace tde

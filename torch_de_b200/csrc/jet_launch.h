@@ -3,6 +3,7 @@
 #include "jet_common.cuh"
 #include "jet_forward_tc.cuh"
 #include "jet_backward_tc.cuh"
+#include "jet_pair_tc.cuh"
 
 // (NF, SMASK) list. SMASK bits enumerate pairs (0,0),(0,1),..,(1,1),.. over the NF first-order channels.
 #define TDE_SPEC_LIST(X) \
@@ -25,7 +26,8 @@ typedef cudaError_t (*TcBwdLauncher)(const TcBwdParams&, int grid, int smem, cud
     cudaError_t launch_forward_##nf##_##sm(const JetParams&, int, int, cudaStream_t);     \
     cudaError_t launch_backward_##nf##_##sm(const JetParams&, int, int, cudaStream_t);     \
     cudaError_t launch_forward_tc_##nf##_##sm(const TcParams&, int, int, cudaStream_t);   \
-    cudaError_t launch_backward_tc_##nf##_##sm(const TcBwdParams&, int, int, cudaStream_t);
+    cudaError_t launch_backward_tc_##nf##_##sm(const TcBwdParams&, int, int, cudaStream_t); \
+    int pair_max_clusters_##nf##_##sm(int smem);
 TDE_SPEC_LIST(TDE_DECL)
 #undef TDE_DECL
 }  // namespace tde

@@ -5,6 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -67,10 +70,40 @@ struct Dispatch {
     tde::JetLauncher fwd, bwd;
     tde::TcLauncher fwd_tc;
     tde::TcBwdLauncher bwd_tc;
+    int (*pair_max_clusters)(int smem);
 };
-#define TDE_ROW(nf, sm) {nf, sm, tde::launch_forward_##nf##_##sm, tde::launch_backward_##nf##_##sm, tde::launch_forward_tc_##nf##_##sm, tde::launch_backward_tc_##nf##_##sm},
+#define TDE_ROW(nf, sm) {nf, sm, tde::launch_forward_##nf##_##sm, tde::launch_backward_##nf##_##sm, tde::launch_forward_tc_##nf##_##sm, tde::launch_backward_tc_##nf##_##sm, tde::pair_max_clusters_##nf##_##sm},
 const Dispatch kDispatch[] = {TDE_SPEC_LIST(TDE_ROW)};
 #undef TDE_ROW
+
+// resident-cluster capacity of the pair kernels, cached per (spec, smem)
+int sm_count();
+
+int pair_cluster_capacity(const Dispatch* d, int smem) {
+    static std::mutex mu;
+    static std::map<std::pair<const Dispatch*, int>, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(d, smem);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const int n = d->pair_max_clusters(smem);
+    cache[key] = n;
+    return n;
+}
+
+// clusters of the tensor-core kernels that can run at once: SMs / cluster size, for the pair kernels at most what the
+// occupancy query reports (planning without a device assumes the full 37)
+int tc_cluster_slots(const Dispatch* d, bool pair, int smem) {
+    const int cl = pair ? tde::kPairCluster : tde::kTcCluster;
+    int slots = sm_count() / cl;
+    if (pair && tde::kPairCluster > 2) {
+        const int cap = pair_cluster_capacity(d, smem);
+        if (cap > 0) slots = std::min(slots, cap);
+        else (void)cudaGetLastError();
+    }
+    if (const char* e = getenv("TDE_TC_SLOTS")) slots = std::min(slots, std::max(1, atoi(e)));   // experiments only
+    return std::max(1, slots);
+}
 
 const Dispatch* find_dispatch(int nf, int smask) {
     for (const Dispatch& d : kDispatch)
@@ -91,7 +124,7 @@ struct Geometry {
     // packed weight offsets
     int64_t o_w_in, o_b_in, o_wt, o_wn, o_bh, o_wo, o_bo, o_wc, packed_floats;
     // tcgen05 forward (wide layers)
-    int use_tc, tc_mb, tc_stages, tc_smem, tc_nacc;
+    int use_tc, use_pair, tc_mb, tc_stages, tc_smem, tc_nacc;
     int use_tc_bwd, dw_smem;
     int64_t o_wct, o_hbar, o_zst, grid_b1, grid_b2;
     int64_t tc_tiles;
@@ -100,7 +133,8 @@ struct Geometry {
     int64_t o_gpart;
     int64_t workspace_floats;
     int64_t stash_floats, stash_layer_stride;
-    int64_t g_dup_lo, g_dup_hi;
+    int n_copies;
+    int64_t g_dup_lo[4], g_dup_hi[4];
     int64_t n_params;
     const Dispatch* disp;
 };
@@ -233,14 +267,21 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         const int Ntc = tde::kTcPoints * g.J;
         const int mb = g.W / 128;
         const char* no_tc = getenv("TDE_NO_TC");
-        if ((g.W == 128 || g.W == 256) && L >= 2 && mb * Ntc <= 512 && g.TP % tde::kTcPoints == 0 && !(no_tc && no_tc[0] == '1')) {
+        // W = 128: single-CTA kernels, N = 16 J columns per MMA.  W = 256: CTA-pair kernels (cta_group::2), N = 32 J <= 256.
+        // TDE_TC_PAIR=1 (W = 256, N = 32 J <= 256): CTA-pair kernels (cta_group::2) instead of the single-CTA ones
+        const char* pair_env = getenv("TDE_TC_PAIR");
+        g.use_pair = g.W == 256 && 2 * Ntc <= 256 && pair_env && pair_env[0] == '1';
+        const bool shape_ok = (g.W == 128 || g.W == 256) && mb * Ntc <= 512;
+        if (shape_ok && L >= 2 && g.TP % tde::kTcPoints == 0 && !(no_tc && no_tc[0] == '1')) {
             const int64_t atomk = (Ntc / 8) * 1024;
-            const int64_t fixed = 1024 + 2 * (g.W / 32) * atomk + 4 * ((int64_t)g.n_out * g.W + tde::kTcPoints * g.d_in + (int64_t)g.J * g.n_out * tde::kTcPoints);
-            const int64_t chunk = (int64_t)mb * 2 * 2 * 2048;
-            for (int st = tde::kMaxStages; st >= 2; --st)
+            const int pts = g.use_pair ? 2 * tde::kTcPoints : tde::kTcPoints;     // points staged per CTA (x, seeds)
+            const int64_t fixed = 1024 + 2 * (g.W / 32) * atomk + 4 * ((int64_t)g.n_out * g.W + pts * g.d_in + (int64_t)g.J * g.n_out * pts);
+            const int64_t chunk = g.use_pair ? tde::kPairChunkBytes : (int64_t)mb * 2 * 2 * 2048;
+            for (int st = tde::kTcMaxStages; st >= 2; --st)
                 if (fixed + st * chunk <= kSmemLimit) {
+                    if (const char* fs = getenv("TDE_TC_STAGES")) st = std::max(2, std::min(st, atoi(fs)));   // experiments only
                     g.use_tc = 1; g.tc_mb = mb; g.tc_stages = st; g.tc_smem = (int)(fixed + st * chunk);
-                    g.tc_nacc = std::min(3, 512 / (mb * Ntc));
+                    g.tc_nacc = std::min(3, 512 / (g.use_pair ? 2 * Ntc : mb * Ntc));
                     break;
                 }
         }
@@ -267,14 +308,20 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.g_bh = q;     q += (int64_t)(L - 1) * g.W;
     g.g_wo = q;     q = align_up(q + (int64_t)g.n_out * g.W, 4);
     g.g_bo = q;     q = align_up(q + g.n_out, 4);
-    g.g_dup_lo = g.g_dup_hi = 0;
+    g.n_copies = 1;
+    for (int k = 0; k < 4; ++k) g.g_dup_lo[k] = g.g_dup_hi[k] = 0;
     if (g.use_tc_bwd) {
-        // the tcgen05 reverse sweep has two threads per neuron (one per half of a tile's points): the second one adds into
-        // its own copy of (w_in | b_in) and (b_hidden | w_out); the reduction sums both copies in a fixed order
+        // the tcgen05 reverse sweep has several threads per neuron (one per group of 8 points: 2 for W = 128, 4 for the CTA
+        // pair): each adds into its own copy of (w_in | b_in) and (b_hidden | w_out); the reduction sums the copies in a
+        // fixed order
+        g.n_copies = g.use_pair ? 4 : 2;
         const int64_t small_end = q;
-        g.g_dup_lo = q;                                  // copy of [0, g_hidden)
-        g.g_dup_hi = q + g.g_hidden - g.g_bh;            // copy of [g_bh, small_end) starts at q + g_hidden
-        q = align_up(q + g.g_hidden + (small_end - g.g_bh), 4);
+        const int64_t dup_size = align_up(g.g_hidden + (small_end - g.g_bh), 4);
+        for (int k = 1; k < g.n_copies; ++k) {
+            g.g_dup_lo[k] = q;                                  // copy of [0, g_hidden)
+            g.g_dup_hi[k] = q + g.g_hidden - g.g_bh;            // copy of [g_bh, small_end) starts at q + g_hidden
+            q += dup_size;
+        }
     }
     g.gp_stride = q;
     g.o_gpart = g.packed_floats;
@@ -282,7 +329,8 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     // padding (x = 0, seeds = 0) and needs real stash rows behind it.
     g.stash_layer_stride = g.n_tiles * g.W * (int64_t)g.TP * g.J;
     if (g.use_tc) {
-        const int64_t padded = (g.tc_tiles + tde::kTcCluster - 1) / tde::kTcCluster * tde::kTcCluster;
+        const int cl = g.use_pair ? tde::kPairCluster : tde::kTcCluster;
+        const int64_t padded = (g.tc_tiles + cl - 1) / cl * cl;
         g.stash_layer_stride = std::max<int64_t>(g.stash_layer_stride, padded * tde::kTcPoints * (int64_t)g.J * g.W);
     }
     g.stash_floats = (int64_t)L * g.stash_layer_stride;
@@ -292,8 +340,9 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         g.o_hbar = g.workspace_floats;
         g.o_zst = g.o_hbar + g.stash_floats;
         g.workspace_floats = g.o_zst + g.stash_floats;
-        const int64_t pairs = (g.tc_tiles + tde::kTcCluster - 1) / tde::kTcCluster;
-        g.grid_b1 = tde::kTcCluster * std::max<int64_t>(1, std::min<int64_t>(sm_count() / tde::kTcCluster, pairs));
+        const int cl = g.use_pair ? tde::kPairCluster : tde::kTcCluster;
+        const int64_t groups = (g.tc_tiles + cl - 1) / cl;
+        g.grid_b1 = cl * std::max<int64_t>(1, std::min<int64_t>(tc_cluster_slots(g.disp, g.use_pair != 0, g.tc_smem), groups));
         g.grid_b2 = std::max<int64_t>(1, std::min<int64_t>(sm_count(), g.tc_tiles));
     }
 
@@ -444,7 +493,8 @@ struct ReduceArgs {
     int n_layers, W, width, d_in, n_out, rsplit, n_active, n_active_hidden;
     int64_t n_params, gp_stride;
     int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo;
-    int64_t dup_lo, dup_hi;      // second copy of the small sections (tcgen05 reverse sweep), 0 if absent
+    int n_copies;                // copies of the small sections (tcgen05 reverse sweep: one per thread of a neuron)
+    int64_t dup_lo[4], dup_hi[4];
     float scale;
 };
 
@@ -490,12 +540,12 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
     }
     float s = 0.0f;
     const int n_slabs = splits > 1 || src >= a.g_hidden && src < a.g_bh ? a.n_active_hidden : a.n_active;
-    int64_t dup = 0;
-    if (a.dup_lo) dup = src < a.g_hidden ? a.dup_lo : (src >= a.g_bh && src < a.g_bo ? a.dup_hi : 0);
+    const int which = src < a.g_hidden ? 1 : (src >= a.g_bh && src < a.g_bo ? 2 : 0);
     for (int c = 0; c < n_slabs; ++c) {
         const float* slab = gpart + (int64_t)c * a.gp_stride + src;
         for (int q = 0; q < splits; ++q) s += slab[(int64_t)q * WW];
-        if (dup) s += slab[dup];
+        if (which)
+            for (int k = 1; k < a.n_copies; ++k) s += slab[which == 1 ? a.dup_lo[k] : a.dup_hi[k]];
     }
     flat[i] += a.scale * s;
 }
@@ -707,7 +757,7 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
     if (g.use_tc) {
         tde::TcParams t{};
         t.x = x; t.B = n_points; t.n_tiles = g.tc_tiles;
-        t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb; t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc; t.fourier_half = g.fourier_half;
+        t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb; t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc; t.fourier_half = g.fourier_half; t.pair = g.use_pair;
         { const char* d = getenv("TDE_TC_DBG"); t.dbg = d ? atoi(d) : 0; }
         static long long* dbg_buf = nullptr;
         if (t.dbg & 4) {
@@ -721,8 +771,9 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
         t.stash_layer_stride = g.stash_layer_stride;
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
         // clusters of kTcCluster CTAs: even grid, never more clusters than tile pairs
-        const int64_t pairs = (g.tc_tiles + tde::kTcCluster - 1) / tde::kTcCluster;
-        const int grid = (int)(tde::kTcCluster * std::max<int64_t>(1, std::min<int64_t>(sm_count() / tde::kTcCluster, pairs)));
+        const int cl = g.use_pair ? tde::kPairCluster : tde::kTcCluster;
+        const int64_t groups = (g.tc_tiles + cl - 1) / cl;
+        const int grid = (int)(cl * std::max<int64_t>(1, std::min<int64_t>(tc_cluster_slots(g.disp, g.use_pair != 0, g.tc_smem), groups)));
         {
             ScopedTimer timer(st, 0);
             TDE_CUDA(g.disp->fwd_tc(t, grid, g.tc_smem, st));
@@ -766,7 +817,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         tde::TcBwdParams t{};
         t.x = x; t.B = n_points; t.n_tiles = g.tc_tiles;
         t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb;
-        t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc; t.fourier_half = g.fourier_half;
+        t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc; t.fourier_half = g.fourier_half; t.pair = g.use_pair;
         for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
         t.wct = ws + g.o_wct; t.w_out = ws + g.o_wo;
         t.seeds = seeds; t.ld_seeds = ld_seeds; t.stash = stash;
@@ -775,7 +826,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
         t.gpart = ws + g.o_gpart; t.gp_stride = g.gp_stride;
         t.gp_off_b_in = g.g_b_in; t.gp_off_b_hidden = g.g_bh; t.gp_off_w_out = g.g_wo; t.gp_off_b_out = g.g_bo;
-        t.gp_dup_lo = g.g_dup_lo; t.gp_dup_hi = g.g_dup_hi;
+        for (int k = 0; k < 4; ++k) { t.gp_dup_lo[k] = g.g_dup_lo[k]; t.gp_dup_hi[k] = g.g_dup_hi[k]; }
         tde::TcDwParams d{};
         d.n_tiles = g.tc_tiles; d.L = g.L; d.W = g.W; d.MB = g.tc_mb; d.J = g.J;
         d.hbar = t.hbar; d.zst = t.zst; d.stash_layer_stride = t.stash_layer_stride; d.tiles_per_bw_tile = t.tiles_per_bw_tile;
@@ -811,7 +862,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
             }
         }
         g_launches += 3;
-        n_active = (int)g.grid_b1;
+        n_active = g.use_pair ? (int)g.grid_b1 / 2 : (int)g.grid_b1;     // a CTA pair shares one slab
         n_active_hidden = (int)g.grid_b2;
     } else {
         tde::JetParams p;
@@ -828,7 +879,8 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
     r.n_layers = net->n_layers; r.W = g.W; r.width = g.width; r.d_in = g.d_in; r.n_out = g.n_out;
     r.rsplit = g.rsplit; r.n_active = n_active; r.n_active_hidden = n_active_hidden; r.n_params = g.n_params; r.gp_stride = g.gp_stride;
     r.g_b_in = g.g_b_in; r.g_hidden = g.g_hidden; r.g_bh = g.g_bh; r.g_wo = g.g_wo; r.g_bo = g.g_bo;
-    r.dup_lo = n_active_hidden ? g.g_dup_lo : 0; r.dup_hi = n_active_hidden ? g.g_dup_hi : 0;
+    r.n_copies = g.n_copies;
+    for (int k = 0; k < 4; ++k) { r.dup_lo[k] = g.g_dup_lo[k]; r.dup_hi[k] = g.g_dup_hi[k]; }
     r.scale = grad_scale;
     const int threads = 256;
     reduce_grads_kernel<<<(int)((g.n_params + threads - 1) / threads), threads, 0, st>>>(r, ws + g.o_gpart, flat_grad);
