@@ -351,15 +351,15 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
 // ---------------------------------------------------------------------------------------------------------------------
 // dW_l = Hbar_l^T-contract Z_{l-1} on the tensor cores
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDwThreads = 640;       // warp 1: MMA issuer, warps 4..11: Hbar loaders + flushers, warps 12..19: Z loaders (one thread per neuron)
-constexpr int kDwStages = 6;          // operand stages, one 8-column k-step each
-constexpr int kDwAhead = 5;           // register-buffered k-steps a loader thread keeps in flight
+constexpr int kDwThreads = 640;       // warp 0: stream producer, warp 1: MMA issuer, warps 4..11: Hbar splitters + flushers, warps 12..19: Z splitters
+constexpr int kDwStages = 4;          // operand stages (hi/lo split, UMMA core-matrix order), one 8-column k-step each
+constexpr int kDwRaw = 5;             // raw FP32 stages filled by cp.async.bulk: 8 columns x W neurons of Hbar and of Z
 constexpr int kDwFlushTiles = 8;      // accumulator is flushed to the slab after this many 16-point tiles
 
 struct TcDwParams {
     int64_t n_tiles;                  // 16-point tiles
     int L, W, MB, J;
-    const float* hbar;                // [L][bw tiles][cols][W]
+    const float* hbar;                // [L][tile][cols][W]
     const float* zst;
     int64_t stash_layer_stride;
     int tiles_per_bw_tile;
@@ -367,6 +367,11 @@ struct TcDwParams {
     int64_t gp_stride, gp_off_hidden;
 };
 
+// Data path: one producer thread streams the two FP32 streams with cp.async.bulk (8 columns = one contiguous 8*W*4 B segment
+// per stream and k-step) into a ring of raw stages.  (Register-buffered loads by the splitter threads were latency-bound: a
+// warp has only six scoreboards, so waiting for the oldest of six load groups also waited for the newest.)  One splitter
+// thread per neuron and stream reads its 8 values from the raw stage, splits them 3xTF32 and writes them as K-major UMMA core
+// matrices into the operand ring.
 template <int UNUSED>
 __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_constant__ TcDwParams p) {
     extern __shared__ __align__(1024) unsigned char smem_tc[];
@@ -374,15 +379,20 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
     const int W = p.W, MB = p.MB;
     const int N = 16 * p.J;                       // jet columns per tile
     const int n_ks = N / 8;                       // k-steps per tile
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);       // [kDwStages] loaders -> MMA (count = loader warps)
-    uint64_t* empty = full + kDwStages;                            // MMA -> loaders (tcgen05.commit)
-    uint64_t* acc_done = empty + kDwStages;                        // MMA -> flushers
-    uint64_t* acc_free = acc_done + 1;                             // flushers -> MMA (count = loader warps)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);       // [kDwStages] splitters -> MMA (count = splitter warps)
+    uint64_t* empty = full + kDwStages;                            // MMA -> splitters (tcgen05.commit)
+    uint64_t* raw_full = empty + kDwStages;                        // [kDwRaw] producer (complete_tx) -> splitters
+    uint64_t* raw_empty = raw_full + kDwRaw;                       // splitters -> producer (count = splitter warps)
+    uint64_t* acc_done = raw_empty + kDwRaw;                       // MMA -> flushers
+    uint64_t* acc_free = acc_done + 1;                             // flushers -> MMA (count = Hbar splitter warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
-    // stage: A_hi | A_lo | B_hi | B_lo, each W rows x 8 k as K-major SWIZZLE_NONE core matrices: [kgroup 2][W/8 row groups][8][4]
+    // operand stage: A_hi | A_lo | B_hi | B_lo, each W rows x 8 k as K-major SWIZZLE_NONE core matrices: [kgroup 2][W/8 row groups][8][4]
     const uint32_t op_bytes = (uint32_t)W * 8u * 4u;
     const uint32_t stage_bytes = 4u * op_bytes;
     unsigned char* stages = smem_raw + 1024;
+    // raw stage: Hbar [8 cols][W] | Z [8 cols][W]
+    const uint32_t raw_bytes = 2u * op_bytes;
+    unsigned char* raws = stages + (size_t)kDwStages * stage_bytes;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_ld_warps = 4 * MB;          // per operand
@@ -390,6 +400,10 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
         for (int s = 0; s < kDwStages; ++s) {
             mbar_init(&full[s], 2 * n_ld_warps);
             mbar_init(&empty[s], 1);
+        }
+        for (int r = 0; r < kDwRaw; ++r) {
+            mbar_init(&raw_full[r], 1);
+            mbar_init(&raw_empty[r], 2 * n_ld_warps);
         }
         mbar_init(acc_done, 1);
         mbar_init(acc_free, n_ld_warps);
@@ -408,7 +422,30 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
     const int64_t my_tiles = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
     if (warp < 4) {
-        if (warp == 1) {
+        if (tid == 0) {
+            // ===== producer: both streams, layer by layer, tile by tile, k-step by k-step =====
+            int r = 0;
+            uint32_t rph = 0;
+            for (int l = 1; l < p.L; ++l) {
+                const float* hsrc = p.hbar + (size_t)l * p.stash_layer_stride;
+                const float* zsrc = p.zst + (size_t)(l - 1) * p.stash_layer_stride;
+                for (int64_t t = 0; t < my_tiles; ++t) {
+                    const int64_t tile = blockIdx.x + t * gridDim.x;
+                    const size_t base = (size_t)tile * N * W;
+                    for (int ks = 0; ks < n_ks; ++ks) {
+                        mbar_wait(&raw_empty[r], rph ^ 1);
+                        mbar_expect_tx(&raw_full[r], raw_bytes);
+                        unsigned char* dst = raws + (size_t)r * raw_bytes;
+                        bulk_g2s(dst, hsrc + base + (size_t)ks * 8 * W, op_bytes, &raw_full[r]);
+                        bulk_g2s(dst + op_bytes, zsrc + base + (size_t)ks * 8 * W, op_bytes, &raw_full[r]);
+                        if (++r == kDwRaw) {
+                            r = 0;
+                            rph ^= 1;
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
             const bool leader = elect_one();
             // D = F32, A = B = TF32 K-major, N = W (k neurons), M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(W >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -454,43 +491,38 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
             }
         }
     } else {
-        const int which = (warp - 4) >> 3;        // 0: Hbar loader (+ flusher), 1: Z loader
+        const int which = (warp - 4) >> 3;        // 0: Hbar splitter (+ flusher), 1: Z splitter
         const int e = (warp - 4) & 7;
         if (e < n_ld_warps) {
             const int quarter = warp & 3;
             const int mb = e >> 2;
-            const int n = mb * 128 + quarter * 32 + lane;    // neuron loaded by this thread; TMEM lane it flushes
+            const int n = mb * 128 + quarter * 32 + lane;    // neuron handled by this thread; TMEM lane it flushes
             float* gp = p.gpart + (size_t)blockIdx.x * p.gp_stride + p.gp_off_hidden;
             // byte offset of row n inside an operand block: [kgroup][row group][row][4 k]
             const uint32_t rowoff = (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u;
             const uint32_t lbo = (uint32_t)(W / 8) * 128u;
-            int s = 0;
-            uint32_t ph = 0, done_ph = 0;
+            int s = 0, r = 0;
+            uint32_t ph = 0, rph = 0, done_ph = 0;
             bool first_flush_of_layer;
             for (int l = 1; l < p.L; ++l) {
                 first_flush_of_layer = true;
-                const float* hsrc = p.hbar + (size_t)l * p.stash_layer_stride;
-                const float* zsrc = p.zst + (size_t)(l - 1) * p.stash_layer_stride;
                 for (int64_t t0 = 0; t0 < my_tiles; t0 += kDwFlushTiles) {
                     const int64_t t1 = t0 + kDwFlushTiles < my_tiles ? t0 + kDwFlushTiles : my_tiles;
-                    // Loads run kDwAhead stages ahead of the stores (ring of kDwAhead + 1 register buffers): the bytes in flight
-                    // per SM (512 loader threads x kDwAhead x 32 B) have to cover the HBM latency at the rate the MMAs consume.
                     const int total = (int)(t1 - t0) * n_ks;
-                    int64_t lt = t0;       // load cursor: tile, k-step
-                    int lks = 0;
-                    float hv[kDwAhead + 1][8];
-                    const float* src = which ? zsrc : hsrc;
-                    auto issue_loads = [&](float (&h8)[8]) {
-                        const int64_t tile = blockIdx.x + lt * gridDim.x;
-                        const size_t row0 = ((size_t)tile * N + (size_t)lks * 8) * W + n;
+                    for (int j = 0; j < total; ++j) {
+                        // my 8 values of this k-step from the raw stage
+                        mbar_wait(&raw_full[r], rph);
+                        const float* rawp = reinterpret_cast<const float*>(raws + (size_t)r * raw_bytes + (size_t)which * op_bytes) + n;
+                        float h8[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) h8[c] = __ldcs(src + row0 + (size_t)c * W);
-                        if (++lks == n_ks) {
-                            lks = 0;
-                            ++lt;
+                        for (int c = 0; c < 8; ++c) h8[c] = rawp[c * W];
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&raw_empty[r]);
+                        if (++r == kDwRaw) {
+                            r = 0;
+                            rph ^= 1;
                         }
-                    };
-                    auto store_stage = [&](const float (&h8)[8]) {
+                        // split and lay out as operand
                         mbar_wait(&empty[s], ph ^ 1);
                         unsigned char* st = stages + (size_t)s * stage_bytes + (size_t)which * 2 * op_bytes;   // A_hi|A_lo or B_hi|B_lo
 #pragma unroll
@@ -511,20 +543,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                             s = 0;
                             ph ^= 1;
                         }
-                    };
-#pragma unroll
-                    for (int b = 0; b < kDwAhead; ++b)
-                        if (b < total) issue_loads(hv[b]);
-                    for (int j = 0; j < total; j += kDwAhead + 1) {
-#pragma unroll
-                        for (int b = 0; b < kDwAhead + 1; ++b) {
-                            if (j + b < total) {
-                                if (j + b + kDwAhead < total) issue_loads(hv[(b + kDwAhead) % (kDwAhead + 1)]);
-                                store_stage(hv[b]);
-                            }
-                        }
                     }
-                    if (which) continue;      // Z loaders do not own TMEM lanes
+                    if (which) continue;      // Z splitters do not own TMEM lanes
                     // ---- flush the accumulator rows of this thread's neuron into the slab ----
                     mbar_wait(acc_done, done_ph);
                     done_ph ^= 1;

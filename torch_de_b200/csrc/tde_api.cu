@@ -292,7 +292,7 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.use_tc_bwd = 0;
     {
         const char* no_b = getenv("TDE_NO_TC_BWD");
-        g.dw_smem = 1024 + tde::kDwStages * 4 * g.W * 32;
+        g.dw_smem = 1024 + (tde::kDwStages * 4 + tde::kDwRaw * 2) * g.W * 32;
         if (g.use_tc && g.dw_smem <= kSmemLimit && !(no_b && no_b[0] == '1')) {
             g.use_tc_bwd = 1;
             g.rsplit = 1;      // the FFMA dW phase (and its column split) is not used on this path
