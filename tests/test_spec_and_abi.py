@@ -87,8 +87,9 @@ def test_plan_geometry_without_a_device():
     assert p.n_tiles == -(-500_000 // p.tile_points)
     assert p.smem_forward <= 232448 and p.smem_backward <= 232448
     exact = 8 * p.n_tiles * 256 * p.tile_points * 5 * 4
-    # the tensor-core kernels may pad the last cluster's tiles (at most 3 tiles of 16 points per layer)
-    assert exact <= p.stash_bytes <= exact + 8 * 3 * 16 * 5 * 256 * 4
+    pad = 8 * 3 * 16 * 5 * 256 * 4     # the tensor-core kernels may pad the last cluster's tiles (at most 3 tiles of 16 points per layer)
+    # tensor-core backward: the forward also keeps the post-activation jets (second half of the stash buffer)
+    assert exact <= p.stash_bytes <= exact + pad or 2 * exact <= p.stash_bytes <= 2 * (exact + pad)
     r = _runner(1, 1, 200, 0, ['u_t', 'u_tt'], ['t'], ['u'])
     p = r.plan(1001)
     assert p.width_padded == 256 and p.n_params == 601 and p.n_channels == 3

@@ -197,7 +197,6 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     const size_t loff = (size_t)l * p.stash_layer_stride + row0;
                     const float* srow_h = p.stash + loff;
                     float* hrow_h = p.hbar + loff;
-                    float* zrow_h = p.zst + loff;
                     uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -225,7 +224,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     const float* xs_h = xs + ph * 8 * p.d_in;
                     const float* seeds_h = seeds_s + ph * 8;
                     {
-                        asm volatile("" : "+l"(srow_h), "+l"(hrow_h), "+l"(zrow_h));
+                        asm volatile("" : "+l"(srow_h), "+l"(hrow_h));
 #pragma unroll
                         for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
 #pragma unroll
@@ -269,7 +268,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
 #pragma unroll
                                     for (int c = 0; c < J; ++c) zb[c] = zbg[q * J + c];
                                 }
-                                act_backward<S, true>(layer_act(p.act, p.fourier_half, l, n), st, zb, hb, z);
+                                act_backward<S, last>(layer_act(p.act, p.fourier_half, l, n), st, zb, hb, z);     // Z_l was written by the forward pass
                                 db += hb[0];
                                 if (last) {
 #pragma unroll
@@ -301,10 +300,6 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                                         for (int i = 0; i < TDE_MAX_IN; ++i)
                                             if (i == p.first_in[a]) dw_in[i] += hb[1 + a];
                                     }
-                                }
-                                if constexpr (KIND != 2) {
-#pragma unroll
-                                    for (int c = 0; c < J; ++c) __stcs(zrow_h + (size_t)(pt8 * J + c) * W, z[c]);
                                 }
                             }
                         }

@@ -317,8 +317,10 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
             constexpr int GC = kTcGroup * J;          // jet columns per 4-point step
             auto layer_body = [&](auto first_c, auto stash_c, const int l) {
                 constexpr bool kFirst = decltype(first_c)::value;     // input layer (no GEMM) vs hidden layers
-                constexpr bool kStash = decltype(stash_c)::value;
+                constexpr int kMode = decltype(stash_c)::value;     // 0: no stash, 1: stash, 2: stash + Z stream
+                constexpr bool kStash = kMode >= 1;
                 float* srow_h = kStash ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
+                float* zrow_h = kMode == 2 ? p.zst + (stash_row - p.stash) + (size_t)l * p.stash_layer_stride : nullptr;
                 uint32_t zaddr[8];      // cluster address of (column & 7 == j, k = n) in the destination hi plane
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                 const float* xs_h = xs + pq * 8 * p.d_in;
                 if (stamp) dst[1] = clock64();
                 if constexpr (kStash) asm volatile("" : "+l"(srow_h));
+                if constexpr (kMode == 2) asm volatile("" : "+l"(zrow_h));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
 #pragma unroll
@@ -387,6 +390,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                         for (int c = 0; c < J; ++c) {
                             const int col8 = pt8 * J + c;           // column within my 8 points (compile-time)
                             if constexpr (kStash) __stcs(srow_h + (size_t)col8 * W, h[c]);      // one 128 B line per warp store
+                                if constexpr (kMode == 2)      // (the last layer's Z is not needed; writing it anyway keeps the loop branch-free)
+                                    __stcs(zrow_h + (size_t)col8 * W, z[c]);
                             float hi, lo;
                             split_tf32(z[c], hi, lo);
                             const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
@@ -406,12 +411,15 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                 }
                 if (stamp) dst[3] = clock64();
             };
-            if (stash_row) {
-                layer_body(std::true_type{}, std::true_type{}, 0);
-                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::true_type{}, l);
+            if (stash_row && p.zst) {
+                layer_body(std::true_type{}, std::integral_constant<int, 2>{}, 0);
+                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 2>{}, l);
+            } else if (stash_row) {
+                layer_body(std::true_type{}, std::integral_constant<int, 1>{}, 0);
+                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 1>{}, l);
             } else {
-                layer_body(std::true_type{}, std::false_type{}, 0);
-                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::false_type{}, l);
+                layer_body(std::true_type{}, std::integral_constant<int, 0>{}, 0);
+                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 0>{}, l);
             }
             mbar_wait_cluster(&bars->planes_done, tile_ph);   // every neuron's last-layer z of MY tile is in my planes
 
@@ -568,7 +576,6 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
                 const size_t loff = (size_t)l * p.stash_layer_stride + row0;
                 const float* srow_h = p.stash + loff;
                 float* hrow_h = p.hbar + loff;
-                float* zrow_h = p.zst + loff;
                 uint32_t zaddr[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -595,7 +602,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
                 for (int i = 0; i < TDE_MAX_IN; ++i) dw_in[i] = 0.0f;
                 const float* xs_h = xs + pq * 8 * p.d_in;
                 const float* seeds_h = seeds_s + pq * 8;
-                asm volatile("" : "+l"(srow_h), "+l"(hrow_h), "+l"(zrow_h));
+                asm volatile("" : "+l"(srow_h), "+l"(hrow_h));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
 #pragma unroll
@@ -639,7 +646,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
 #pragma unroll
                             for (int c = 0; c < J; ++c) zb[c] = zbg[q * J + c];
                         }
-                        act_backward<S, true>(layer_act(p.act, p.fourier_half, l, n), st, zb, hb, z);
+                        act_backward<S, last>(layer_act(p.act, p.fourier_half, l, n), st, zb, hb, z);     // Z_l was written by the forward pass
                         db += hb[0];
                         if (last) {
 #pragma unroll
@@ -671,10 +678,6 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
                                 for (int i = 0; i < TDE_MAX_IN; ++i)
                                     if (i == p.first_in[a]) dw_in[i] += hb[1 + a];
                             }
-                        }
-                        if constexpr (KIND != 2) {
-#pragma unroll
-                            for (int c = 0; c < J; ++c) __stcs(zrow_h + (size_t)(pt8 * J + c) * W, z[c]);
                         }
                     }
                 }

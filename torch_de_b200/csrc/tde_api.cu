@@ -132,7 +132,7 @@ struct Geometry {
     int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo, gp_stride;
     int64_t o_gpart;
     int64_t workspace_floats;
-    int64_t stash_floats, stash_layer_stride;
+    int64_t stash_floats, stash_total_floats, stash_layer_stride;
     int n_copies;
     int64_t g_dup_lo[4], g_dup_hi[4];
     int64_t n_params;
@@ -334,12 +334,17 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         g.stash_layer_stride = std::max<int64_t>(g.stash_layer_stride, padded * tde::kTcPoints * (int64_t)g.J * g.W);
     }
     g.stash_floats = (int64_t)L * g.stash_layer_stride;
+    g.stash_total_floats = g.stash_floats;
     g.workspace_floats = align_up(g.packed_floats + (int64_t)std::max(g.n_ctas, sm_count()) * g.gp_stride, 64);
     g.o_hbar = g.o_zst = 0;
     if (g.use_tc_bwd) {       // Hbar_l and Z_l streams for the tensor-core weight-gradient kernel
+        // Hbar_l stream (written by the reverse sweep, read by the weight-gradient GEMM of the same call) lives in the
+        // workspace; the Z_l stream is written by the FORWARD pass and read by the backward pass, so it travels with the
+        // stash (second half of the caller's stash buffer): another forward on the same workspace must not clobber it
         g.o_hbar = g.workspace_floats;
-        g.o_zst = g.o_hbar + g.stash_floats;
-        g.workspace_floats = g.o_zst + g.stash_floats;
+        g.workspace_floats = g.o_hbar + g.stash_floats;
+        g.o_zst = g.stash_floats;             // offset inside the stash buffer
+        g.stash_total_floats = 2 * g.stash_floats;
         const int cl = g.use_pair ? tde::kPairCluster : tde::kTcCluster;
         const int64_t groups = (g.tc_tiles + cl - 1) / cl;
         g.grid_b1 = cl * std::max<int64_t>(1, std::min<int64_t>(tc_cluster_slots(g.disp, g.use_pair != 0, g.tc_smem), groups));
@@ -730,7 +735,7 @@ int tde_plan(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points, TdePla
     plan->tile_points = g.TP;
     plan->n_ctas = g.n_ctas;
     plan->n_tiles = g.n_tiles;
-    plan->stash_bytes = g.stash_floats * 4;
+    plan->stash_bytes = g.stash_total_floats * 4;
     plan->workspace_bytes = g.workspace_floats * 4;
     plan->n_params = g.n_params;
     plan->smem_forward = g.smem_fwd;
@@ -768,6 +773,7 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
         t.w_in = ws + g.o_w_in; t.b_in = ws + g.o_b_in; t.wc = ws + g.o_wc; t.b_hidden = ws + g.o_bh;
         t.w_out = ws + g.o_wo; t.b_out = ws + g.o_bo;
         t.out = out; t.ld_out = ld_out; t.stash = stash;
+        t.zst = stash && g.use_tc_bwd ? stash + g.o_zst : nullptr;     // second half of the stash buffer
         t.stash_layer_stride = g.stash_layer_stride;
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
         // clusters of kTcCluster CTAs: even grid, never more clusters than tile pairs
@@ -821,7 +827,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
         t.wct = ws + g.o_wct; t.w_out = ws + g.o_wo;
         t.seeds = seeds; t.ld_seeds = ld_seeds; t.stash = stash;
-        t.hbar = ws + g.o_hbar; t.zst = ws + g.o_zst;
+        t.hbar = ws + g.o_hbar; t.zst = const_cast<float*>(stash) + g.o_zst;
         t.stash_layer_stride = g.stash_layer_stride;
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
         t.gpart = ws + g.o_gpart; t.gp_stride = g.gp_stride;
