@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)i * W);
                     uint32_t taddr = 0;
                     if (!last) {
-                        mbar_wait(&acc_ready[mb], acc_ph);
+                        mbar_wait_park(&acc_ready[mb], acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
                         taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N + ph * 2 * GC);
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
 constexpr int kDwThreads = 640;       // warp 0: stream producer, warp 1: MMA issuer, warps 4..11: Hbar splitters + flushers, warps 12..19: Z splitters
 constexpr int kDwStages = 4;          // operand stages (hi/lo split, UMMA core-matrix order), one 8-column k-step each
 constexpr int kDwRaw = 5;             // raw FP32 stages filled by cp.async.bulk: 8 columns x W neurons of Hbar and of Z
-constexpr int kDwFlushTiles = 8;      // accumulator is flushed to the slab after this many 16-point tiles
+constexpr int kDwFlushTiles = 24;     // accumulator is flushed to the slab after this many 16-point tiles (720 accumulations per chain)
 
 struct TcDwParams {
     int64_t n_tiles;                  // 16-point tiles
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                     const int total = (int)(t1 - t0) * n_ks;
                     for (int j = 0; j < total; ++j) {
                         // my 8 values of this k-step from the raw stage
-                        mbar_wait(&raw_full[r], rph);
+                        mbar_wait_park(&raw_full[r], rph);
                         const float* rawp = reinterpret_cast<const float*>(raws + (size_t)r * raw_bytes + (size_t)which * op_bytes) + n;
                         float h8[8];
 #pragma unroll
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                             rph ^= 1;
                         }
                         // split and lay out as operand
-                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_wait_park(&empty[s], ph ^ 1);
                         unsigned char* st = stages + (size_t)s * stage_bytes + (size_t)which * 2 * op_bytes;   // A_hi|A_lo or B_hi|B_lo
 #pragma unroll
                         for (int kg = 0; kg < 2; ++kg) {

@@ -175,6 +175,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// many-warp wait (epilogue warps waiting for the MMAs): the suspend-time hint parks the warp in hardware until the phase
+// completes instead of re-issuing try_wait / branch / yield -- those spin instructions were 41% of all issued instructions
+__device__ __forceinline__ void mbar_wait_park(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT_P:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE_P;\n"
+        "bra LAB_WAIT_P;\n"
+        "DONE_P:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
 // producer-side wait: long hardware suspend + nanosleep back-off (one thread; must not burn issue slots)
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;

@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                         for (int a = 0; a < NF; ++a) wf[a] = __ldg(p.w_in + n * p.d_in + p.first_in[a]);
                     } else {
                         bn = __ldg(p.b_hidden + (size_t)(l - 1) * W + n);
-                        mbar_wait(&acc_ready[mb], acc_ph);
+                        mbar_wait_park(&acc_ready[mb], acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
                         taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N + ph * 2 * GC);

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                     for (int a = 0; a < NF; ++a) wf[a] = __ldg(p.w_in + n * p.d_in + p.first_in[a]);
                 } else {
                     bn = __ldg(p.b_hidden + (size_t)(l - 1) * W + n);
-                    mbar_wait(&bars->acc_ready, acc_ph);
+                    mbar_wait_park(&bars->acc_ready, acc_ph);
                     acc_ph ^= 1;
                     tc_fence_after();
                     taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pq * 2 * GC);
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
                 for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)i * W);
                 uint32_t taddr = 0;
                 if (!last) {
-                    mbar_wait(&bars->acc_ready, acc_ph);
+                    mbar_wait_park(&bars->acc_ready, acc_ph);
                     acc_ph ^= 1;
                     tc_fence_after();
                     taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pq * 2 * GC);
