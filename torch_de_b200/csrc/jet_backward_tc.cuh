@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                 // rows for it, so it runs the same code and contributes exact zeros
                 const int64_t tile = pair * kTcCluster + crank;
                 const int64_t pbase = tile * kTcPoints;
+                const bool tstamp = p.dbg_buf && blockIdx.x == 0 && et == 0 && pair == first_pair + 3 * pair_step;
+                if (tstamp) p.dbg_buf[40] = clock64();      // tile start
                 for (int i = et; i < kTcPoints * p.d_in; i += n_epi) {
                     const int64_t gpt = pbase + i / p.d_in;
                     xs[i] = gpt < p.B ? p.x[gpt * p.d_in + (i % p.d_in)] : 0.0f;
@@ -177,6 +179,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     seeds_s[i] = gpt < p.B ? p.seeds[(size_t)r * p.ld_seeds + gpt] : 0.0f;
                 }
                 epi_sync();
+                if (tstamp) p.dbg_buf[41] = clock64();      // inputs staged
                 const size_t row0 = ((size_t)tile * N + (size_t)ph * (8 * J)) * W + n;     // [layer][tile][jet column][neuron]
 
                 // Epilogue as 2 x (2 steps of 4 points): 8 points are unrolled so every shared/global offset is an immediate (a
@@ -204,9 +207,13 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && ph == 0 && pair == first_pair + 3 * pair_step && l >= 3 && l <= 5;
                     long long* const dst = p.dbg_buf + 16 + ((5 - l) * 2 + mb) * 4;   // steady-state tile, both neuron blocks
                     if (stamp) dst[0] = clock64();
-                    float st_next[GC];
+                    // all of this thread's stash values of the layer are requested before the wait for the accumulators, so their
+                    // latency hides under the MMAs (a later prefetch would share a scoreboard with younger loads and stall)
+                    float stv[2][GC];
 #pragma unroll
-                    for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)i * W);
+                    for (int g = 0; g < 2; ++g)
+#pragma unroll
+                        for (int i = 0; i < GC; ++i) stv[g][i] = __ldcs(srow_h + (size_t)(g * GC + i) * W);
                     uint32_t taddr = 0;
                     if (!last) {
                         mbar_wait_park(&acc_ready[mb], acc_ph);
@@ -229,24 +236,19 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                         for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
 #pragma unroll
                         for (int g2 = 0; g2 < 2; ++g2) {
-                            float stg[GC], zbg[GC];
-#pragma unroll
-                            for (int i = 0; i < GC; ++i) stg[i] = st_next[i];
-                            if (g2 == 0) {
-#pragma unroll
-                                for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)(GC + i) * W);
-                            }
+                            float zbg[GC];
+                            const float (&stg)[GC] = stv[g2];
                             if (!last) {
-                                float cur[kAccSets][GC];
-#pragma unroll
-                                for (int a = 0; a < kAccSets; ++a) tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + g2 * GC), cur[a]);
+                                // one accumulator set at a time: at most 2 x GC registers in flight next to the stash values
+                                tmem_ld_cols<GC>(taddr + (uint32_t)(g2 * GC), zbg);
                                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                                for (int i = 0; i < GC; ++i) {
-                                    float v = cur[0][i];
+                                for (int a = 1; a < kAccSets; ++a) {
+                                    float cur[GC];
+                                    tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + g2 * GC), cur);
+                                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                                    for (int a = 1; a < kAccSets; ++a) v += cur[a][i];
-                                    zbg[i] = v;
+                                    for (int i = 0; i < GC; ++i) zbg[i] += cur[i];
                                 }
                             }
 #pragma unroll
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     slab_add(gp + p.gp_off_b_out + et, s, first);
                 }
                 epi_sync();   // xs / seeds_s are rewritten by the next tile
+                if (tstamp) p.dbg_buf[44] = clock64();      // tile done
             }
         }
     }

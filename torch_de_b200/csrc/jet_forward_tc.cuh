@@ -402,11 +402,14 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
                 const int64_t tile = pair * kTcCluster + crank;     // may be a padding tile (>= n_tiles, all points >= B)
                 const int64_t pbase = tile * kTcPoints;
+                const bool tstamp = p.dbg_buf && blockIdx.x == 0 && et == 0 && pair == first_pair + 3 * pair_step;
+                if (tstamp) p.dbg_buf[40] = clock64();      // tile start
                 for (int i = et; i < kTcPoints * p.d_in; i += n_epi) {
                     const int64_t gp = pbase + i / p.d_in;
                     xs[i] = gp < p.B ? p.x[gp * p.d_in + (i % p.d_in)] : 0.0f;
                 }
                 epi_sync();
+                if (tstamp) p.dbg_buf[41] = clock64();      // inputs staged
                 // [layer][tile][jet column][neuron]: this thread's neuron, first column of the tile.  A padding tile (the second
                 // tile of the last pair when the tile count is odd) has stash rows of its own and x = 0.
                 float* const stash_row = p.stash ? p.stash + ((size_t)tile * N + (size_t)ph * (8 * J)) * W + n : nullptr;
@@ -524,14 +527,17 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                     for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 0>{}, l);
                 }
                 epi_sync();   // every neuron's last-layer z is in the planes
+                if (tstamp) p.dbg_buf[42] = clock64();      // last layer's epilogue done everywhere
 
-                // ---- output layer: one thread per jet column, z = hi + lo ----
-                for (int col = et; col < N; col += n_epi) {
+                // ---- output layer: kOutParts lanes per jet column split the K = W reduction, z = hi + lo ----
+                constexpr int kOutParts = N * 8 <= n_epi ? 8 : (N * 4 <= n_epi ? 4 : (N * 2 <= n_epi ? 2 : 1));
+                if (et < N * kOutParts) {
+                    const int col = et / kOutParts, part = et % kOutParts;
                     float y[TDE_MAX_OUT];
 #pragma unroll
                     for (int o = 0; o < TDE_MAX_OUT; ++o) y[o] = 0.0f;
                     const uint32_t cbase = (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u;
-                    for (int kg = 0; kg < W / 4; ++kg) {
+                    for (int kg = part; kg < W / 4; kg += kOutParts) {
                         const uint32_t o4 = (uint32_t)(kg >> 3) * ATOMK + cbase + ((((uint32_t)kg & 7u) ^ (uint32_t)(col & 7)) << 4);
                         const float4 a = *reinterpret_cast<const float4*>(zhi + o4);
                         const float4 b = *reinterpret_cast<const float4*>(zlo + o4);
@@ -543,18 +549,26 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                                 for (int i = 0; i < 4; ++i) y[o] = fmaf(zz[i], wout_s[o * W + kg * 4 + i], y[o]);
                             }
                     }
-                    const int pt = col / J, c = col - pt * J;
 #pragma unroll
                     for (int o = 0; o < TDE_MAX_OUT; ++o)
-                        if (o < p.n_out) ybuf[(c * p.n_out + o) * kTcPoints + pt] = y[o] + (c == 0 ? __ldg(p.b_out + o) : 0.0f);
+#pragma unroll
+                        for (int d = 1; d < kOutParts; d <<= 1) y[o] += __shfl_xor_sync(0xffffffffu, y[o], d);
+                    if (part == 0) {
+                        const int pt = col / J, c = col - pt * J;
+#pragma unroll
+                        for (int o = 0; o < TDE_MAX_OUT; ++o)
+                            if (o < p.n_out) ybuf[(c * p.n_out + o) * kTcPoints + pt] = y[o] + (c == 0 ? __ldg(p.b_out + o) : 0.0f);
+                    }
                 }
                 epi_sync();
+                if (tstamp) p.dbg_buf[43] = clock64();      // output layer computed
                 for (int i = et; i < J * p.n_out * kTcPoints; i += n_epi) {
                     const int r = i / kTcPoints, pt = i - r * kTcPoints;
                     const int64_t gp = pbase + pt;
                     if (gp < p.B) p.out[(size_t)r * p.ld_out + gp] = ybuf[i];
                 }
                 epi_sync();
+                if (tstamp) p.dbg_buf[44] = clock64();      // tile done
             }
         }
     }

@@ -795,6 +795,8 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
                     fprintf(stderr, "[tc dbg] fwd layer %d block %d: start %lld  acc_ready %lld  body_end %lld  published %lld\n", l + 2, b,
                             d[0] - h[16], d[1] - h[16], d[2] - h[16], d[3] - h[16]);
                 }
+            fprintf(stderr, "[tc dbg] fwd tile: inputs staged %lld  last epilogue done %lld  output layer %lld  tile done %lld | layer-2 start %lld\n",
+                    h[41] - h[40], h[42] - h[40], h[43] - h[40], h[44] - h[40], h[16] - h[40]);
         }
     } else {
         tde::JetParams p;
@@ -857,6 +859,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
                     fprintf(stderr, "[tc dbg] bwd layer %d block %d: start %lld  acc_ready %lld  body_end %lld  published %lld\n", 5 - l, b,
                             d[0] - h[16], d[1] - h[16], d[2] - h[16], d[3] - h[16]);
                 }
+            fprintf(stderr, "[tc dbg] bwd tile: inputs staged %lld  tile done %lld | layer-5 start %lld\n", h[41] - h[40], h[44] - h[40], h[16] - h[40]);
         }
         {
             ScopedTimer timer(st, 2);
