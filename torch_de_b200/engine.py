@@ -54,6 +54,7 @@ class JetRunner:
         self._net.n_layers = len(self.lins)
         self._plans: Dict[int, _lib.TdePlan] = {}
         self._workspace: Optional[torch.Tensor] = None
+        self._chunk_stash: Optional[torch.Tensor] = None
         self.chunking: Dict[tuple, int] = {}
 
     def _bind(self, tensors: Sequence[torch.Tensor]):
@@ -106,7 +107,9 @@ class JetRunner:
                 raise RuntimeError(f"network parameters live on {p.device} but the input is on {x.device}")
         return x.contiguous()
 
-    def forward(self, x: torch.Tensor, tensors: Sequence[torch.Tensor], need_stash: bool):
+    def forward(self, x: torch.Tensor, tensors: Sequence[torch.Tensor], need_stash: bool, reuse_stash: bool = False):
+        """reuse_stash: keep the stash in a buffer owned by the runner (recompute mode: it only lives until the matching
+        backward of the same chunk, and re-allocating ~100 GB blocks every chunk fragments the caching allocator)."""
         x = self._check_x(x)
         B = x.shape[0]
         out = torch.empty((self.ch.n_rows, B), dtype=torch.float32, device=x.device)
@@ -114,7 +117,14 @@ class JetRunner:
             return x, out, None
         plan = self.plan(B)
         self._bind(tensors)
-        stash = torch.empty(plan.stash_bytes // 4, dtype=torch.float32, device=x.device) if need_stash else None
+        stash = None
+        if need_stash and reuse_stash:
+            if self._chunk_stash is None or self._chunk_stash.numel() < plan.stash_bytes // 4 or self._chunk_stash.device != x.device:
+                self._chunk_stash = None
+                self._chunk_stash = torch.empty(plan.stash_bytes // 4, dtype=torch.float32, device=x.device)
+            stash = self._chunk_stash
+        elif need_stash:
+            stash = torch.empty(plan.stash_bytes // 4, dtype=torch.float32, device=x.device)
         ws = self._ws(plan.workspace_bytes, x.device)
         rc = _lib.lib().tde_jet_forward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, out.data_ptr(), B,
                                         stash.data_ptr() if need_stash else None, ws.data_ptr(), self._stream(x.device))
@@ -203,7 +213,7 @@ class _JetFunction(torch.autograd.Function):
             grad_out = grad_out.contiguous()
             for lo in range(0, B, ctx.chunk):
                 hi = min(B, lo + ctx.chunk)
-                xc, _, stash = runner.forward(x[lo:hi], params, need_stash=True)
+                xc, _, stash = runner.forward(x[lo:hi], params, need_stash=True, reuse_stash=True)
                 runner.backward(xc, params, stash, grad_out[:, lo:hi], flat_grad=flat, seeds_ld=B)
                 del stash
         return (None, None, *runner.split_flat(flat))
