@@ -274,7 +274,10 @@ __device__ __forceinline__ void tc_issue_layer(const bool leader, const uint32_t
 
 constexpr int kTcGroup = 4;        // points handled per unrolled epilogue step (16 points = 4 steps)
 // accumulator sets that fit the 512 TMEM columns (3: cross terms | main even k-steps | main odd k-steps)
-__host__ __device__ constexpr int tc_acc_sets(int mb, int n) { return 512 / (mb * n) >= 3 ? 3 : 512 / (mb * n); }
+#ifndef TDE_MAX_ACC_SETS
+#define TDE_MAX_ACC_SETS 3
+#endif
+__host__ __device__ constexpr int tc_acc_sets(int mb, int n) { return 512 / (mb * n) >= TDE_MAX_ACC_SETS ? TDE_MAX_ACC_SETS : 512 / (mb * n); }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 template <int NF, int SMASK, int W>

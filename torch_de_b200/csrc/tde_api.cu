@@ -281,7 +281,7 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
                 if (fixed + st * chunk <= kSmemLimit) {
                     if (const char* fs = getenv("TDE_TC_STAGES")) st = std::max(2, std::min(st, atoi(fs)));   // experiments only
                     g.use_tc = 1; g.tc_mb = mb; g.tc_stages = st; g.tc_smem = (int)(fixed + st * chunk);
-                    g.tc_nacc = std::min(3, 512 / (g.use_pair ? 2 * Ntc : mb * Ntc));
+                    g.tc_nacc = tde::tc_acc_sets(g.use_pair ? 1 : mb, g.use_pair ? 2 * Ntc : Ntc);
                     break;
                 }
         }
