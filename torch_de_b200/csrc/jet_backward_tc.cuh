@@ -53,7 +53,6 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
     using S = JetSpecT<NF, SMASK>;
     constexpr int J = S::J;
     constexpr int N = kTcPoints * J;
-    constexpr uint32_t ATOMK = (N / 8) * 1024;
     extern __shared__ __align__(1024) unsigned char smem_tc[];
     unsigned char* const smem_raw = smem_tc;
 
@@ -65,12 +64,11 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
     uint64_t* act_ready = empty + kTcMaxStages;
     uint64_t* acc_ready = act_ready + 2;     // [neuron block]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
-    unsigned char* zhi = smem_raw + 1024;
-    constexpr uint32_t z_plane_c = (uint32_t)(W / 32) * ATOMK;
-    const uint32_t z_plane = z_plane_c;
-    unsigned char* zlo = zhi + z_plane;
+    using P = TcPlanes<N>;
+    unsigned char* zpl = smem_raw + 1024;                   // Hbar planes: [k-atom][hi | lo part][column group][8 x 128 B]
+    constexpr uint32_t z_planes = (uint32_t)(W / 32) * P::kAtom;
     const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;
-    unsigned char* wst = zlo + z_plane;
+    unsigned char* wst = zpl + z_planes;
     float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
     float* xs = wout_s + p.n_out * W;                 // [16][d_in]
     float* seeds_s = xs + kTcPoints * p.d_in;         // [J*n_out][16]
@@ -129,17 +127,15 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
         } else if (warp == 1) {
             // ===== MMA issuer (warp converged, one elected lane) =====
             const bool leader = elect_one();
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint64_t b_hi0 = umma_desc_sw128(smem_u32(zhi), 1024);
-            const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
+            const uint64_t b0 = umma_desc_sw128(smem_u32(zpl), 1024);
             const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
             const uint32_t stage_step = chunk_bytes >> 4;
             int s = 0;
             uint32_t ph = 0, act_ph = 0;
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step)
                 for (int l = p.L - 1; l >= 1; --l)
-                    tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, idesc, a0, b_hi0, b_lo0, stage_step, full, empty, act_ready, acc_ready,
-                                                    n_stages, n_ks, s, ph, act_ph);
+                    tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, a0, b0, stage_step, full, empty, act_ready, acc_ready,
+                                                    n_stages, s, ph, act_ph);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tc_epi_regs(W)));
@@ -153,7 +149,9 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
             auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory"); };
 
             for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
-            const uint32_t zrow = (uint32_t)(n >> 5) * ATOMK + (uint32_t)(n & 3) * 4u;
+            const uint32_t hoff = P::template hi_off<kAccSets>((uint32_t)n >> 5);
+            const uint32_t zrow = (uint32_t)(n >> 5) * P::kAtom + hoff + (uint32_t)(n & 3) * 4u;
+            const uint32_t lo_delta = P::kHalf - 2u * hoff;
             const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;
             // the two threads of a neuron (one per point half) add into separate copies of the small gradient sections
             float* gp = p.gpart + (size_t)blockIdx.x * p.gp_stride;
@@ -203,7 +201,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        zaddr[j] = smem_u32(zhi) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph * (uint32_t)(J * 1024);
+                        zaddr[j] = smem_u32(zpl) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph * (uint32_t)(J * 1024);
                     const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && ph == 0 && pair == first_pair + 3 * pair_step && l >= 3 && l <= 5;
                     long long* const dst = p.dbg_buf + 16 + ((5 - l) * 2 + mb) * 4;   // steady-state tile, both neuron blocks
                     if (stamp) dst[0] = clock64();
@@ -219,7 +217,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                         mbar_wait_park(&acc_ready[mb], acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
-                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N + ph * 2 * GC);
+                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * kAccSets * N + ph * 2 * GC);
                     }
                     if (stamp) dst[1] = clock64();
                     float db = 0.0f;
@@ -245,7 +243,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
 #pragma unroll
                                 for (int a = 1; a < kAccSets; ++a) {
                                     float cur[GC];
-                                    tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + g2 * GC), cur);
+                                    tmem_ld_cols<GC>(taddr + (uint32_t)(a * N + g2 * GC), cur);
                                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                                     for (int i = 0; i < GC; ++i) zbg[i] += cur[i];
@@ -288,7 +286,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                                         split_tf32(hb[c], hi, lo);
                                         const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
                                         sts_f32(a, hi);
-                                        sts_f32(a + z_plane_c, lo);
+                                        sts_f32(a + lo_delta, lo);
                                     }
                                 } else {
                                     // input layer: h = W0 x + b0, h_a = W0[:, first_in[a]]

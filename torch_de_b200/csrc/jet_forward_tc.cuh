@@ -12,6 +12,7 @@
 // Roles: warp 0 weight producer, warp 1 MMA issuer (one elected thread), warps 4.. epilogue (1 thread per neuron).
 #pragma once
 #include <type_traits>
+#include <utility>
 #include "jet_common.cuh"
 
 namespace tde {
@@ -189,33 +190,77 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
 // One layer's GEMM, issued by the converged MMA warp (one elected lane issues, the whole warp runs the control flow: a
 // tcgen05.mma inside divergent code is wrapped by the compiler in an ELECT/branch loop of ~100 cycles each).
 //
-// The tensor core rounds its FP32 accumulator toward zero after every MMA: that bias, not the TF32 split, limits accuracy.
-// The 2^-11-sized cross terms get their own accumulator set and the main term alternates over two sets; the epilogue adds
-// them in FP32 (RN).
+// Accuracy: the tensor core rounds its FP32 accumulator toward zero after every MMA; that bias, not the TF32 split, limits
+// accuracy.  The 2^-11-sized cross terms get their own accumulator set and the main term alternates over two sets (by
+// k-atom of 32 inputs); the epilogue adds them in FP32 (RN).  TMEM columns of neuron block mb: [main even | cross | main odd]
+// (3 sets, N columns each) or [main | cross] (2 sets when 3 do not fit).
+//
+// Shared-memory traffic: these kernels are bound by the 128 B/clk of shared memory (MMA operand reads + weight-stage fills +
+// epilogue stores = 15 k cycles per layer and tile with three MMAs per k-step).  A_hi x B_hi and A_hi x B_lo are therefore
+// ONE MMA of N = 2 x 16J columns over the operand [B_hi | B_lo]: the activation planes keep, per k-atom, the 16J/8 column
+// groups of hi and of lo next to each other (odd k-atoms in the order [lo | hi], so that the result lands on
+// [cross | main odd]).  A_hi is read once instead of twice: 23.5 KB instead of 27.5 KB per k-step and neuron block.
 //
 // W = 256 (MB = 2): the layer is issued as four quarters (neuron block mb, input half kh) in the order
 //   (0,0) (1,0) (0,1) (1,1), and each neuron block has its own act_ready / acc_ready barrier pair.  Quarter (0,0) needs only
 // the new activations of neurons 0..127 and the drained accumulators of block 0, so it runs while the epilogue warps of
 // block 1 still work on the previous layer; block 0's accumulators are complete after the third quarter, so its epilogue
 // runs under the fourth.  The weight image is packed in exactly this order (one 16 KB chunk = one block, two k-steps).
+template <int N>
+struct TcPlanes {
+    static constexpr uint32_t kHalf = (N / 8) * 1024;      // bytes of one part (hi or lo) of a k-atom: N/8 column groups
+    static constexpr uint32_t kAtom = 2 * kHalf;           // bytes of a k-atom (32 inputs): both parts
+    // byte offset of the hi part inside k-atom j; the lo part is the other half
+    template <int kAccSets>
+    __device__ static __forceinline__ uint32_t hi_off(const uint32_t j) { return kAccSets == 3 && (j & 1u) ? kHalf : 0u; }
+};
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+// f(integral_constant<int, 0>) ... f(integral_constant<int, COUNT - 1>)
+template <int COUNT, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    static_for_impl(f, std::make_integer_sequence<int, COUNT>{});
+}
+// The issue loop is fully unrolled (k-step, neuron block and k-atom parity are compile-time) and the descriptors are built
+// from a constant high word and a 32-bit low word: the first version spent ~460 cycles per 16 KB chunk in 64-bit descriptor
+// arithmetic on the uniform datapath -- more than the six MMAs of the chunk take -- and that, not the tensor pipe, set the
+// length of the MMA phase.
 template <int MB, int N, int kAccSets>
-__device__ __forceinline__ void tc_issue_layer(const bool leader, const uint32_t tmem_base, const uint32_t idesc, const uint64_t a0,
-                                               const uint64_t b_hi0, const uint64_t b_lo0, const uint32_t stage_step, uint64_t* full,
-                                               uint64_t* empty, uint64_t* act_ready, uint64_t* acc_ready, const int n_stages, const int n_ks,
-                                               int& s, uint32_t& ph, uint32_t& act_ph) {
-    constexpr uint32_t ATOMK = (N / 8) * 1024;
-    auto kstep = [&](const int ks, const int mb, const uint64_t a_hi, const uint64_t a_lo) {
-        // k-step ks: atom ks/4, then 32 B (8 tf32) per step inside the 128 B swizzled row
-        const uint32_t koff = ((uint32_t)(ks >> 2) * ATOMK + (uint32_t)(ks & 3) * 32u) >> 4;
-        const uint64_t b_hi = b_hi0 + (uint64_t)koff;
-        const uint64_t b_lo = b_lo0 + (uint64_t)koff;
-        const uint32_t main_set = kAccSets == 3 ? (uint32_t)(1 + (ks & 1)) : (kAccSets == 2 ? 1u : 0u);
-        const uint32_t acc_main = kAccSets == 3 ? (uint32_t)(ks >= 2) : (kAccSets == 2 ? (uint32_t)(ks > 0) : 1u);
-        const uint32_t d_small = tmem_base + (uint32_t)(mb * N);
-        const uint32_t d_main = tmem_base + (uint32_t)((main_set * MB + mb) * N);
-        umma_tf32(d_small, a_lo, b_hi, idesc, ks > 0);
-        umma_tf32(d_small, a_hi, b_lo, idesc, 1);
-        umma_tf32(d_main, a_hi, b_hi, idesc, acc_main);
+__device__ __forceinline__ void tc_issue_layer(const bool leader, const uint32_t tmem_base, const uint64_t a0, const uint64_t b0,
+                                               const uint32_t stage_step, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
+                                               uint64_t* acc_ready, const int n_stages, int& s, uint32_t& ph, uint32_t& act_ph) {
+    using P = TcPlanes<N>;
+    static_assert(kAccSets == 2 || kAccSets == 3, "the merged hi*hi | hi*lo MMA needs a cross-term accumulator set");
+    // instruction descriptors: D = F32, A = B = TF32 K-major, M = 128, N columns / both parts
+    constexpr uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr int n_ks = 16 * MB;           // k-steps of 8 inputs: W / 8
+    const uint32_t a_lo32 = (uint32_t)a0, a_hi32 = (uint32_t)(a0 >> 32), b_lo32 = (uint32_t)b0, b_hi32 = (uint32_t)(b0 >> 32);
+    auto desc = [](const uint32_t lo, const uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
+    // one k-step of neuron block mb; a_stage32: low descriptor word of the hi part of this k-step's weights (lo part: + 4 KB)
+    auto kstep = [&](auto ks_c, auto mb_c, const uint32_t a_stage32) {
+        constexpr int ks = decltype(ks_c)::value, mb = decltype(mb_c)::value;
+        constexpr uint32_t j = (uint32_t)ks >> 2;                                  // k-atom, then 32 B per step inside the 128 B row
+        constexpr uint32_t atom = j * P::kAtom + ((uint32_t)ks & 3u) * 32u;
+        constexpr uint32_t hoff = (kAccSets == 3 && (j & 1u)) ? P::kHalf : 0u;
+        const uint64_t a_hi = desc(a_stage32, a_hi32), a_lo = desc(a_stage32 + (4096u >> 4), a_hi32);
+        const uint64_t b_both = desc(b_lo32 + (atom >> 4), b_hi32);                // [hi | lo], odd atoms: [lo | hi]
+        const uint64_t b_hi = desc(b_lo32 + ((atom + hoff) >> 4), b_hi32);
+        const uint32_t d = tmem_base + (uint32_t)(mb * kAccSets * N);
+        if constexpr (kAccSets == 3 && hoff != 0) {
+            if constexpr (ks == 4) {
+                // first odd k-atom: "main odd" is not initialised yet, the cross set is -- two separate MMAs this once
+                umma_tf32(d + 2 * N, a_hi, b_hi, idesc1, 0);
+                umma_tf32(d + N, a_hi, b_both, idesc1, 1);       // N columns from the start of the atom = B_lo
+            } else {
+                umma_tf32(d + N, a_hi, b_both, idesc2, 1);       // [cross | main odd] += A_hi x [B_lo | B_hi]
+            }
+        } else {
+            umma_tf32(d, a_hi, b_both, idesc2, ks > 0);          // [main (even) | cross] (+)= A_hi x [B_hi | B_lo]
+        }
+        umma_tf32(d + N, a_lo, b_hi, idesc1, 1);                 // cross += A_lo x B_hi
     };
     auto advance = [&]() {
         if (++s == n_stages) {
@@ -226,48 +271,44 @@ __device__ __forceinline__ void tc_issue_layer(const bool leader, const uint32_t
     if constexpr (MB == 1) {
         mbar_wait(&act_ready[0], act_ph);   // planes of the previous layer are in smem, TMEM accumulators are drained
         tc_fence_after();
-        for (int ks = 0; ks < n_ks; ++ks) {
+        static_for<n_ks>([&](auto ks_c) {      // one 8 KB chunk per k-step
             mbar_wait(&full[s], ph);
             tc_fence_after();
             if (leader) {
-                const uint64_t a_stage = a0 + (uint64_t)(s * stage_step);
-                kstep(ks, 0, a_stage, a_stage + (uint64_t)(4096u >> 4));
+                kstep(ks_c, std::integral_constant<int, 0>{}, a_lo32 + (uint32_t)s * stage_step);
                 umma_commit_mc(&empty[s], (uint16_t)((1u << kTcCluster) - 1));   // stage is free in BOTH CTAs' view
             }
             __syncwarp();
             advance();
-        }
+        });
         if (leader) umma_commit(&acc_ready[0]);
         __syncwarp();
     } else {
-        const int ks_half = n_ks / 2;
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-            const int mb = q & 1, kh = q >> 1;
-            if (q < 2) {
+        constexpr int ks_half = n_ks / 2;
+        static_for<4>([&](auto q_c) {
+            constexpr int q = decltype(q_c)::value, mb = q & 1, kh = q >> 1;
+            if constexpr (q < 2) {
                 mbar_wait(&act_ready[q], act_ph);
                 tc_fence_after();
             }
-            for (int cc = 0; cc < ks_half / 2; ++cc) {
+            static_for<ks_half / 2>([&](auto cc_c) {      // 16 KB chunks: one block, two k-steps
+                constexpr int cc = decltype(cc_c)::value;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 if (leader) {
-                    const uint64_t a_stage = a0 + (uint64_t)(s * stage_step);
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; ++s2) {
-                        const uint64_t a_hi = a_stage + (uint64_t)(s2 * (8192 >> 4));
-                        kstep(kh * ks_half + cc * 2 + s2, mb, a_hi, a_hi + (uint64_t)(4096u >> 4));
-                    }
+                    const uint32_t a_stage32 = a_lo32 + (uint32_t)s * stage_step;
+                    kstep(std::integral_constant<int, kh * ks_half + cc * 2>{}, std::integral_constant<int, mb>{}, a_stage32);
+                    kstep(std::integral_constant<int, kh * ks_half + cc * 2 + 1>{}, std::integral_constant<int, mb>{}, a_stage32 + (8192u >> 4));
                     umma_commit_mc(&empty[s], (uint16_t)((1u << kTcCluster) - 1));
                 }
                 __syncwarp();
                 advance();
-            }
-            if (q >= 2) {
+            });
+            if constexpr (q >= 2) {
                 if (leader) umma_commit(&acc_ready[q - 2]);
                 __syncwarp();
             }
-        }
+        });
     }
     act_ph ^= 1;
 }
@@ -278,6 +319,8 @@ constexpr int kTcGroup = 4;        // points handled per unrolled epilogue step 
 #define TDE_MAX_ACC_SETS 3
 #endif
 __host__ __device__ constexpr int tc_acc_sets(int mb, int n) { return 512 / (mb * n) >= TDE_MAX_ACC_SETS ? TDE_MAX_ACC_SETS : 512 / (mb * n); }
+// the single-CTA kernels need a cross-term set (>= 2) and a merged MMA of N = 2 x 16 J <= 256 columns
+__host__ __device__ constexpr bool tc_shape_ok(int mb, int n) { return 2 * n <= 256 && tc_acc_sets(mb, n) >= 2; }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 template <int NF, int SMASK, int W>
@@ -287,7 +330,6 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
     constexpr int N = kTcPoints * J;             // jet columns per tile (multiple of 16)
     // activation planes: K-major SWIZZLE_128B atoms of 8 jet columns x 32 k (1024 B), ordered [k/32][col/8].  A warp's 32
     // consecutive neurons write one full 128 B row per column (conflict-free) and every MMA operand row is 128 B aligned.
-    constexpr uint32_t ATOMK = (N / 8) * 1024;   // bytes between k-atoms
     extern __shared__ __align__(1024) unsigned char smem_tc[];
     unsigned char* const smem_raw = smem_tc;
 
@@ -299,12 +341,11 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
     uint64_t* act_ready = empty + kTcMaxStages;
     uint64_t* acc_ready = act_ready + 2;     // [neuron block]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
-    unsigned char* zhi = smem_raw + 1024;
-    constexpr uint32_t z_plane_c = (uint32_t)(W / 32) * ATOMK;
-    const uint32_t z_plane = z_plane_c;
-    unsigned char* zlo = zhi + z_plane;
+    using P = TcPlanes<N>;
+    unsigned char* zpl = smem_raw + 1024;                            // activation planes: [k-atom][hi | lo part][column group][8 x 128 B]
+    constexpr uint32_t z_planes = (uint32_t)(W / 32) * P::kAtom;
     const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;   // [hi|lo][mb][kgroup 2][16 row groups][8][4] floats*4
-    unsigned char* wst = zlo + z_plane;                              // [n_stages][chunk_bytes]
+    unsigned char* wst = zpl + z_planes;                             // [n_stages][chunk_bytes]
     float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
     float* xs = wout_s + p.n_out * W;            // [16][d_in]
     float* ybuf = xs + kTcPoints * p.d_in;       // [J*n_out][16]
@@ -366,10 +407,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
             // ===== MMA issuer: the whole warp runs the control flow converged, one elected lane issues =====
             // (a UTCHMMA inside divergent code is wrapped by the compiler in an ELECT/branch loop: ~100 cycles each)
             const bool leader = elect_one();
-            // instruction descriptor: D=F32, A=B=TF32, both K-major, N, M=128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint64_t b_hi0 = umma_desc_sw128(smem_u32(zhi), 1024);
-            const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
+            const uint64_t b0 = umma_desc_sw128(smem_u32(zpl), 1024);
             const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
             const uint32_t stage_step = chunk_bytes >> 4;
             int s = 0;
@@ -379,8 +417,8 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                 for (int l = 1; l < p.L; ++l) {
                     const bool mstamp = p.dbg_buf && blockIdx.x == 0 && tile == 0 && l == 2 && lane == 0;
                     if (mstamp) p.dbg_buf[8] = clock64();
-                    tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, idesc, a0, b_hi0, b_lo0, stage_step, full, empty, act_ready, acc_ready,
-                                                    n_stages, n_ks, s, ph, act_ph);
+                    tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, a0, b0, stage_step, full, empty, act_ready, acc_ready,
+                                                    n_stages, s, ph, act_ph);
                     if (mstamp) p.dbg_buf[10] = clock64();
                 }
             }
@@ -398,7 +436,9 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
 
             for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
             // byte offset of element (col, k = n) inside a Z plane
-            const uint32_t zrow = (uint32_t)(n >> 5) * ATOMK + (uint32_t)(n & 3) * 4u;   // k-atom + byte within the 16 B chunk
+            const uint32_t hoff = P::template hi_off<kAccSets>((uint32_t)n >> 5);
+            const uint32_t zrow = (uint32_t)(n >> 5) * P::kAtom + hoff + (uint32_t)(n & 3) * 4u;   // k-atom, hi part, byte within the 16 B chunk
+            const uint32_t lo_delta = P::kHalf - 2u * hoff;                                       // hi -> lo part of the same k-atom (wraps for odd atoms)
             const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;                                // 16 B chunk index before the swizzle
             uint32_t acc_ph = 0;
 
@@ -431,7 +471,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                     uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        zaddr[j] = smem_u32(zhi) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph * (uint32_t)(J * 1024);
+                        zaddr[j] = smem_u32(zpl) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph * (uint32_t)(J * 1024);
                     float wrow[TDE_MAX_IN], wf[NF > 0 ? NF : 1];
                     float bn;
                     uint32_t taddr = 0;
@@ -449,7 +489,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                         mbar_wait_park(&acc_ready[mb], acc_ph);
                         acc_ph ^= 1;
                         tc_fence_after();
-                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * N + ph * 2 * GC);
+                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * kAccSets * N + ph * 2 * GC);
                     }
                     const float* xs_h = xs + ph * 8 * p.d_in;
                     if (stamp) dst[1] = clock64();
@@ -464,7 +504,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                             if constexpr (!kFirst) {
                                 float cur[kAccSets][GC];
 #pragma unroll
-                                for (int a = 0; a < kAccSets; ++a) tmem_ld_cols<GC>(taddr + (uint32_t)(a * MB * N + g2 * GC), cur[a]);
+                                for (int a = 0; a < kAccSets; ++a) tmem_ld_cols<GC>(taddr + (uint32_t)(a * N + g2 * GC), cur[a]);
                                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                                 for (int i = 0; i < GC; ++i) {
@@ -504,7 +544,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                                     split_tf32(z[c], hi, lo);
                                     const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
                                     sts_f32(a, hi);
-                                    sts_f32(a + z_plane_c, lo);
+                                    sts_f32(a + lo_delta, lo);
                                 }
                             }
                         }
@@ -541,9 +581,10 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                     for (int o = 0; o < TDE_MAX_OUT; ++o) y[o] = 0.0f;
                     const uint32_t cbase = (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u;
                     for (int kg = part; kg < W / 4; kg += kOutParts) {
-                        const uint32_t o4 = (uint32_t)(kg >> 3) * ATOMK + cbase + ((((uint32_t)kg & 7u) ^ (uint32_t)(col & 7)) << 4);
-                        const float4 a = *reinterpret_cast<const float4*>(zhi + o4);
-                        const float4 b = *reinterpret_cast<const float4*>(zlo + o4);
+                        const uint32_t ho = P::template hi_off<kAccSets>((uint32_t)kg >> 3);
+                        const uint32_t o4 = (uint32_t)(kg >> 3) * P::kAtom + cbase + ((((uint32_t)kg & 7u) ^ (uint32_t)(col & 7)) << 4);
+                        const float4 a = *reinterpret_cast<const float4*>(zpl + o4 + ho);
+                        const float4 b = *reinterpret_cast<const float4*>(zpl + o4 + (P::kHalf - ho));
                         const float zz[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
 #pragma unroll
                         for (int o = 0; o < TDE_MAX_OUT; ++o)

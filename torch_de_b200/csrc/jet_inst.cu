@@ -11,6 +11,17 @@
 
 namespace tde {
 
+// single-CTA tensor-core kernels exist where the merged N = 2 x 16 J MMA and a cross-term accumulator set fit
+template <int NF, int SMASK, int W, bool OK = tc_shape_ok(W / 128, kTcPoints * JetSpecT<NF, SMASK>::J)>
+struct TcKernels {
+    static void (*fwd())(TcParams) { return jet_forward_tc_kernel<NF, SMASK, W>; }
+    static void (*bwd())(TcBwdParams) { return jet_backward_tc_kernel<NF, SMASK, W>; }
+};
+template <int NF, int SMASK, int W>
+struct TcKernels<NF, SMASK, W, false> {
+    static void (*fwd())(TcParams) { return nullptr; }
+    static void (*bwd())(TcBwdParams) { return nullptr; }
+};
 // CTA-pair kernels exist for jet specs with N = 32 J <= 256 only
 template <int NF, int SMASK, bool OK = (JetSpecT<NF, SMASK>::J <= 8)>
 struct PairKernels {
@@ -40,7 +51,7 @@ cudaError_t TDE_CAT(launch_backward_, TDE_NF, _, TDE_SMASK)(const JetParams& p, 
 }
 
 cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p, int grid, int smem, cudaStream_t st) {
-    void (*k)(TcParams) = p.W == 256 ? jet_forward_tc_kernel<TDE_NF, TDE_SMASK, 256> : jet_forward_tc_kernel<TDE_NF, TDE_SMASK, 128>;
+    void (*k)(TcParams) = p.W == 256 ? TcKernels<TDE_NF, TDE_SMASK, 256>::fwd() : TcKernels<TDE_NF, TDE_SMASK, 128>::fwd();
     int threads = tc_threads(p.W), cluster = kTcCluster;
     if (p.pair) {
         k = PairKernels<TDE_NF, TDE_SMASK>::fwd();
@@ -48,6 +59,7 @@ cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p,
         cluster = kPairCluster;
         if (!k) return cudaErrorInvalidValue;
     }
+    if (!k) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
@@ -66,7 +78,7 @@ cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p,
 }
 
 cudaError_t TDE_CAT(launch_backward_tc_, TDE_NF, _, TDE_SMASK)(const TcBwdParams& p, int grid, int smem, cudaStream_t st) {
-    void (*k)(TcBwdParams) = p.W == 256 ? jet_backward_tc_kernel<TDE_NF, TDE_SMASK, 256> : jet_backward_tc_kernel<TDE_NF, TDE_SMASK, 128>;
+    void (*k)(TcBwdParams) = p.W == 256 ? TcKernels<TDE_NF, TDE_SMASK, 256>::bwd() : TcKernels<TDE_NF, TDE_SMASK, 128>::bwd();
     int threads = tc_threads(p.W), cluster = kTcCluster;
     if (p.pair) {
         k = PairKernels<TDE_NF, TDE_SMASK>::bwd();
@@ -74,6 +86,7 @@ cudaError_t TDE_CAT(launch_backward_tc_, TDE_NF, _, TDE_SMASK)(const TcBwdParams
         cluster = kPairCluster;
         if (!k) return cudaErrorInvalidValue;
     }
+    if (!k) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
