@@ -22,8 +22,8 @@ struct TcKernels<NF, SMASK, W, false> {
     static void (*fwd())(TcParams) { return nullptr; }
     static void (*bwd())(TcBwdParams) { return nullptr; }
 };
-// CTA-pair kernels exist for jet specs with N = 32 J <= 256 only
-template <int NF, int SMASK, bool OK = (JetSpecT<NF, SMASK>::J <= 8)>
+// CTA-pair kernels exist for jet specs with 96 J <= 512 TMEM columns only
+template <int NF, int SMASK, bool OK = (JetSpecT<NF, SMASK>::J <= 5)>
 struct PairKernels {
     static void (*fwd())(TcParams) { return jet_forward_pair_kernel<NF, SMASK>; }
     static void (*bwd())(TcBwdParams) { return jet_backward_pair_kernel<NF, SMASK>; }

@@ -1,22 +1,22 @@
-// tcgen05 CTA-pair kernels for W = 256: forward pass and reverse sweep with `cta_group::2` MMAs.
+// tcgen05 CTA-pair kernels for W = 256 (J <= 5): forward pass and reverse sweep with `cta_group::2` MMAs.
 //
-// Why a pair: in the single-CTA kernels every 16-point tile streams the full 512 KB (hi + lo) weight image of a layer into
-// shared memory, and an SM takes in ~42 B/clk from L2 -- 12 k cycles per layer and tile, more than the MMAs need.  Here two
-// CTAs (one cluster, two SMs of a TPC) share one layer GEMM of 32 points:
-//
-//   D[256 neurons][2 x 16*J columns] = W_l[256][256] * Z[256][2 x 16*J]        M = 256, N = 32*J, K = 8 per MMA
-//
+// Two CTAs (one cluster, two SMs of a TPC) share every layer GEMM of a 32-point pair tile, M = 256 neurons over both CTAs:
 //   * CTA r owns neurons 128r .. 128r+127: it streams only ITS rows of the weights (A operand) and its TMEM holds their
-//     accumulators for all 32 points -> 4x fewer weight bytes per point and SM than the single-CTA kernel;
-//   * CTA r keeps the activation planes (B operand, K-major SWIZZLE_128B, hi and lo) of ITS 16 points; the MMA reads half of
-//     the N columns from each CTA;
-//   * epilogue thread = (neuron, 8 of the 32 points): it writes the new activation row of its neuron into the planes of the
-//     CTA that owns those points -- its own shared memory or the peer's (st.shared::cluster);
+//     accumulators -> half the weight bytes and half the A-operand reads per point and SM of the single-CTA kernel;
+//   * CTA r keeps the activation planes (B operand, K-major SWIZZLE_128B) of ITS 16 points; the MMA reads half of its N
+//     columns from each CTA;
+//   * the pair tile is worked as two SUB-TILES of 2 x 8 points with their own TMEM regions and barriers: while the epilogue
+//     warps of one sub-tile run, the MMAs of the other one do (per sub-tile the chain MMA -> epilogue -> MMA is serial);
+//   * per k-step and sub-tile two MMAs: A_hi x [B_hi | B_lo] (N = 32 J: each CTA supplies the 8J hi and the 8J lo columns of
+//     its 8 points, stored next to each other) and A_lo x B_hi (N = 16 J).  TMEM region of a sub-tile (48 J columns):
+//     [c0 main | c0 hi*lo | c1 main | c1 hi*lo][c0 lo*hi | c1 lo*hi]; the epilogue adds the three in FP32;
+//   * epilogue thread = (neuron, 8 points): it writes the new activation row of its neuron into the planes of the CTA that
+//     owns those points -- its own shared memory (st.shared) or the peer's (st.shared::cluster);
 //   * only the leader (rank 0) issues MMAs; the peer's MMA warp relays "my weight stage is full" to the leader.  tcgen05.commit
 //     with a multicast mask releases the weight stage and publishes the accumulators in both CTAs.
 //
-// Everything per-thread (jet activation, 3xTF32 split, stash layout, three accumulator sets against the tensor core's
-// round-toward-zero accumulation) is the same as in jet_forward_tc.cuh / jet_backward_tc.cuh.
+// The main term accumulates over all 32 k-steps in one accumulator (no even/odd alternation: 2 x 48 J = 480 of the 512 TMEM
+// columns are taken): worst stream error 6.5e-6 instead of 3.7e-6 (bar: 1e-5), the same as the FFMA path.
 #pragma once
 #include "jet_backward_tc.cuh"
 
@@ -102,61 +102,76 @@ struct PairBars {
     uint64_t full[kTcMaxStages];        // producer -> MMA: my weight stage landed
     uint64_t empty[kTcMaxStages];       // MMA (commit, both CTAs) -> producer
     uint64_t peer_full[kTcMaxStages];   // leader only: the peer's stage landed (relayed by the peer's warp 1)
-    uint64_t act_ready;                 // leader only: 32 epilogue warps (both CTAs) wrote the planes and drained TMEM
-    uint64_t acc_ready;                 // MMA (commit, both CTAs) -> epilogue
+    uint64_t act_ready[2];              // [sub-tile] leader only: its 16 epilogue warps (both CTAs) wrote the planes and drained TMEM
+    uint64_t acc_ready[2];              // [sub-tile] MMA (commit, both CTAs) -> epilogue
     uint64_t planes_done;               // forward: the 16 warps (8 per CTA) that write MY planes finished the last layer
     uint64_t planes_free[2];            // forward: CTA d finished reading its planes (output layer); one arrival from CTA d
     uint32_t tmem_slot;
 };
 
-// MMA issue for one layer by the leader's converged warp 1 (see tc_issue_layer for the accumulator-set scheme)
-template <int N2, int NT, int kAccSets>
-__device__ __forceinline__ void pair_issue_layer(const bool leader, const uint32_t tmem_base, const uint32_t idesc, const uint64_t a0,
-                                                 const uint64_t b_hi0, const uint64_t b_lo0, PairBars* bars, const int n_stages, int& s,
-                                                 uint32_t& ph, uint32_t& act_ph, const uint16_t pair_mask, const bool no_weights = false) {
-    constexpr uint32_t ATOMK = (NT / 8) * 1024;
-    mbar_wait_cluster(&bars->act_ready, act_ph);
-    act_ph ^= 1;
-    tc_fence_after();
-    for (int c = 0; c < 16; ++c) {          // 16 chunks x 2 k-steps = K 256
-        if (!no_weights) {      // (timing experiment: MMAs on whatever is in the stages)
-            mbar_wait(&bars->full[s], ph);
-            mbar_wait_relaxed(&bars->peer_full[s], ph);
-        }
+// plane geometry of one CTA: [k-atom of 32 inputs][sub-tile 2][part: hi, lo][J column groups of 8][8 x 128 B]
+template <int J>
+struct PairPlanes {
+    static constexpr uint32_t kPart = (uint32_t)J * 1024u;      // 8J columns of one part
+    static constexpr uint32_t kSub = 2u * kPart;                // hi | lo of a sub-tile
+    static constexpr uint32_t kAtom = 2u * kSub;
+    static constexpr uint32_t kBytes = 8u * kAtom;              // K = 256 inputs
+};
+
+// MMA issue for one layer by the leader's converged warp 1: sub-tile 0 then sub-tile 1, each over all 32 k-steps (the weights
+// stream twice per layer).  Fully unrolled; descriptors = constant high word + 32-bit low word (see tc_issue_layer).
+template <int J>
+__device__ __forceinline__ void pair_issue_layer(const bool leader, const uint32_t tmem_base, const uint64_t a0, const uint64_t b0,
+                                                 PairBars* bars, const int n_stages, int& s, uint32_t& ph, uint32_t& act_ph,
+                                                 const uint16_t pair_mask, const bool no_weights = false) {
+    using P = PairPlanes<J>;
+    constexpr int NS = 8 * J;              // columns of (CTA, sub-tile, part)
+    // D = F32, A = B = TF32 K-major, M = 256 (128 rows per CTA); N = 4 NS (both parts, both CTAs) / 2 NS (hi part, both CTAs)
+    constexpr uint32_t idesc_both = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((4 * NS) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    constexpr uint32_t idesc_hi = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * NS) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t a_lo32 = (uint32_t)a0, a_hi32 = (uint32_t)(a0 >> 32), b_lo32 = (uint32_t)b0, b_hi32 = (uint32_t)(b0 >> 32);
+    auto desc = [](const uint32_t lo, const uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
+    static_for<2>([&](auto t_c) {
+        constexpr int t = decltype(t_c)::value;
+        mbar_wait_cluster(&bars->act_ready[t], act_ph);
         tc_fence_after();
-        if (leader) {
-            const uint64_t a_stage = a0 + (uint64_t)(s * (kPairChunkBytes >> 4));
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const int ks = c * 2 + s2;
-                const uint64_t a_hi = a_stage + (uint64_t)(s2 * (8192 >> 4));
-                const uint64_t a_lo = a_hi + (uint64_t)(4096u >> 4);
-                const uint32_t koff = ((uint32_t)(ks >> 2) * ATOMK + (uint32_t)(ks & 3) * 32u) >> 4;
-                const uint64_t b_hi = b_hi0 + (uint64_t)koff;
-                const uint64_t b_lo = b_lo0 + (uint64_t)koff;
-                const uint32_t main_set = kAccSets == 3 ? (uint32_t)(1 + (ks & 1)) : (kAccSets == 2 ? 1u : 0u);
-                const uint32_t acc_main = kAccSets == 3 ? (uint32_t)(ks >= 2) : (kAccSets == 2 ? (uint32_t)(ks > 0) : 1u);
-                const uint32_t d_small = tmem_base;
-                const uint32_t d_main = tmem_base + main_set * (uint32_t)N2;
-                umma2_tf32(d_small, a_lo, b_hi, idesc, ks > 0);
-                umma2_tf32(d_small, a_hi, b_lo, idesc, 1);
-                umma2_tf32(d_main, a_hi, b_hi, idesc, acc_main);
+        const uint32_t d_both = tmem_base + (uint32_t)(t * 6 * NS), d_lohi = d_both + (uint32_t)(4 * NS);
+        static_for<16>([&](auto c_c) {          // 16 chunks x 2 k-steps = K 256
+            constexpr int c = decltype(c_c)::value;
+            if (!no_weights) {      // (timing experiment: MMAs on whatever is in the stages)
+                mbar_wait(&bars->full[s], ph);
+                mbar_wait_relaxed(&bars->peer_full[s], ph);
             }
-            if (!no_weights) umma2_commit_mc(&bars->empty[s], (uint16_t)((1u << kPairCluster) - 1));     // every CTA of the cluster: with two pairs a stage is rewritten by ranks r and r^2
-        }
+            tc_fence_after();
+            if (leader) {
+                const uint32_t a_stage32 = a_lo32 + (uint32_t)s * (uint32_t)(kPairChunkBytes >> 4);
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int ks = c * 2 + s2;
+                    const uint32_t boff = (uint32_t)(ks >> 2) * P::kAtom + (uint32_t)t * P::kSub + (uint32_t)(ks & 3) * 32u;
+                    const uint64_t b = desc(b_lo32 + (boff >> 4), b_hi32);                 // starts at the hi part of sub-tile t
+                    const uint64_t a_hi = desc(a_stage32 + (uint32_t)(s2 * (8192 >> 4)), a_hi32);
+                    const uint64_t a_lo = desc(a_stage32 + (uint32_t)(s2 * (8192 >> 4)) + (4096u >> 4), a_hi32);
+                    umma2_tf32(d_both, a_hi, b, idesc_both, ks > 0);      // [main | hi*lo] of both CTAs' points
+                    umma2_tf32(d_lohi, a_lo, b, idesc_hi, ks > 0);        // lo*hi
+                }
+                if (!no_weights) umma2_commit_mc(&bars->empty[s], (uint16_t)((1u << kPairCluster) - 1));
+            }
+            __syncwarp();
+            if (++s == n_stages) {
+                s = 0;
+                ph ^= 1;
+            }
+        });
+        if (leader) umma2_commit_mc(&bars->acc_ready[t], pair_mask);
         __syncwarp();
-        if (++s == n_stages) {
-            s = 0;
-            ph ^= 1;
-        }
-    }
-    if (leader) umma2_commit_mc(&bars->acc_ready, pair_mask);
-    __syncwarp();
+    });
+    act_ph ^= 1;
 }
 
 // the peer's warp 1: tell the leader when each of my weight stages has landed
 __device__ __forceinline__ void pair_relay_layer(PairBars* bars, const uint32_t leader_peer_full0, const int n_stages, int& s, uint32_t& ph) {
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < 32; ++c) {          // two passes over the layer's 16 chunks (one per sub-tile)
         mbar_wait(&bars->full[s], ph);
         if ((threadIdx.x & 31) == 0) mbar_arrive_cluster_relaxed(leader_peer_full0 + (uint32_t)s * 8u);
         __syncwarp();
@@ -175,7 +190,8 @@ __device__ __forceinline__ void pair_produce_layer(PairBars* bars, unsigned char
     const uint32_t role = crank4 & 1u, half = crank4 >> 1;
     const uint16_t mask = kPairsPerCluster == 2 ? (uint16_t)((1u << role) | (1u << (role + 2))) : (uint16_t)(1u << role);
     constexpr uint32_t part = kPairChunkBytes / kPairsPerCluster;
-    for (int c = 0; c < 16; ++c) {
+    for (int cc = 0; cc < 32; ++cc) {       // two passes over the layer's 16 chunks (one per sub-tile)
+        const int c = cc & 15;
         mbar_wait(&bars->empty[s], ph ^ 1);
         mbar_expect_tx(&bars->full[s], kPairChunkBytes);
         const int ci = ((c >> 3) * 2 + (int)role) * 8 + (c & 7);
@@ -195,8 +211,10 @@ __device__ __forceinline__ void pair_setup(PairBars* bars, const int n_stages, c
             mbar_init(&bars->empty[s], kPairsPerCluster);     // one commit from each pair's leader
             mbar_init(&bars->peer_full[s], 1);
         }
-        mbar_init(&bars->act_ready, 32);
-        mbar_init(&bars->acc_ready, 1);
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&bars->act_ready[t], 16);
+            mbar_init(&bars->acc_ready[t], 1);
+        }
         mbar_init(&bars->planes_done, 16);
         mbar_init(&bars->planes_free[0], 1);
         mbar_init(&bars->planes_free[1], 1);
@@ -227,17 +245,16 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
     constexpr int W = 256;
     constexpr int J = S::J;
     constexpr int NT = kTcPoints * J;            // jet columns of one CTA's 16-point tile
-    constexpr int N2 = 2 * NT;                   // MMA N: both tiles of the pair
-    constexpr uint32_t ATOMK = (NT / 8) * 1024;
-    constexpr int kAccSets = tc_acc_sets(1, N2);
-    constexpr uint32_t z_plane_c = (uint32_t)(W / 32) * ATOMK;
+    constexpr int NS = 8 * J;                    // jet columns of one CTA's half of a sub-tile (8 points)
+    using P = PairPlanes<J>;
+    static_assert(12 * NS <= 512, "two sub-tile regions of 6 x 8J TMEM columns");
+    constexpr int kAccSets = 3;                  // main | hi*lo | lo*hi
     constexpr int n_epi = 512;
     extern __shared__ __align__(1024) unsigned char smem_tc[];
     unsigned char* const smem_raw = smem_tc;
     PairBars* bars = reinterpret_cast<PairBars*>(smem_raw);
-    unsigned char* zhi = smem_raw + 1024;
-    unsigned char* zlo = zhi + z_plane_c;
-    unsigned char* wst = zlo + z_plane_c;
+    unsigned char* zpl = smem_raw + 1024;            // planes, see PairPlanes
+    unsigned char* wst = zpl + P::kBytes;
     const int n_stages = p.n_stages;
     float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * kPairChunkBytes);   // [n_out][W]
     float* xs = wout_s + p.n_out * W;                // [32][d_in]: both tiles of the pair
@@ -266,14 +283,11 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
             uint32_t ph = 0, act_ph = 0;
             if (crank == 0) {
                 const bool leader = elect_one();
-                // D = F32, A = B = TF32 K-major, N = N2, M = 256 (128 rows per CTA)
-                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-                const uint64_t b_hi0 = umma_desc_sw128(smem_u32(zhi), 1024);
-                const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
+                const uint64_t b0 = umma_desc_sw128(smem_u32(zpl), 1024);
                 const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
                 for (int64_t quad = first_quad; quad < n_quads; quad += quad_step)
                     for (int l = 1; l < p.L; ++l)
-                        pair_issue_layer<N2, NT, kAccSets>(leader, tmem_base, idesc, a0, b_hi0, b_lo0, bars, n_stages, s, ph, act_ph, (uint16_t)(3u << pbase), (p.dbg & 8) != 0);
+                        pair_issue_layer<J>(leader, tmem_base, a0, b0, bars, n_stages, s, ph, act_ph, (uint16_t)(3u << pbase), (p.dbg & 8) != 0);
             } else {
                 const uint32_t leader_peer_full0 = mapa_u32(smem_u32(&bars->peer_full[0]), pbase);
                 for (int64_t quad = first_quad; quad < n_quads && !(p.dbg & 8); quad += quad_step)
@@ -293,10 +307,10 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
 
         for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
         // byte offset of element (col, k = n) inside a plane, then its address in the destination CTA
-        const uint32_t zrow = (uint32_t)(n >> 5) * ATOMK + (uint32_t)(n & 3) * 4u;
+        const uint32_t zrow = (uint32_t)(n >> 5) * P::kAtom + (uint32_t)ph8 * P::kSub + (uint32_t)(n & 3) * 4u;   // k-atom, sub-tile, hi part
         const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;
-        const uint32_t zhi_dest = mapa_u32(smem_u32(zhi), pbase + dest);
-        const uint32_t act_ready_leader = mapa_u32(smem_u32(&bars->act_ready), pbase);
+        const uint32_t zhi_dest = mapa_u32(smem_u32(zpl), pbase + dest);
+        const uint32_t act_ready_leader = mapa_u32(smem_u32(&bars->act_ready[ph8]), pbase);
         const uint32_t planes_done_dest = mapa_u32(smem_u32(&bars->planes_done), pbase + dest);
         const uint32_t planes_free_mine[2] = {mapa_u32(smem_u32(&bars->planes_free[crank]), pbase), mapa_u32(smem_u32(&bars->planes_free[crank]), pbase + 1)};
         uint32_t acc_ph = 0, tile_ph = 0;
@@ -324,7 +338,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                 uint32_t zaddr[8];      // cluster address of (column & 7 == j, k = n) in the destination hi plane
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    zaddr[j] = zhi_dest + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph8 * (uint32_t)(J * 1024);
+                    zaddr[j] = zhi_dest + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u;
                 float wrow[TDE_MAX_IN], wf[NF > 0 ? NF : 1];
                 float bn;
                 uint32_t taddr = 0;
@@ -339,10 +353,10 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                     for (int a = 0; a < NF; ++a) wf[a] = __ldg(p.w_in + n * p.d_in + p.first_in[a]);
                 } else {
                     bn = __ldg(p.b_hidden + (size_t)(l - 1) * W + n);
-                    mbar_wait_park(&bars->acc_ready, acc_ph);
+                    mbar_wait_park(&bars->acc_ready[ph8], acc_ph);
                     acc_ph ^= 1;
                     tc_fence_after();
-                    taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pq * 2 * GC);
+                    taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ph8 * 6 * NS);     // my sub-tile's TMEM region
                 }
                 const float* xs_h = xs + pq * 8 * p.d_in;
                 if (stamp) dst[1] = clock64();
@@ -356,7 +370,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                     if constexpr (!kFirst) {
                         float cur[kAccSets][GC];
 #pragma unroll
-                        for (int a = 0; a < kAccSets; ++a) tmem_ld_cols<GC>(taddr + (uint32_t)(a * N2 + g2 * GC), cur[a]);
+                        for (int a = 0; a < kAccSets; ++a)      // main, hi*lo, lo*hi of my 8 points (owner CTA `dest`)
+                            tmem_ld_cols<GC>(taddr + (a < 2 ? dest * 2 * NS + a * NS : 4 * NS + dest * NS) + (uint32_t)(g2 * GC), cur[a]);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int i = 0; i < GC; ++i) {
@@ -396,7 +411,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                             split_tf32(z[c], hi, lo);
                             const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
                             st_cluster_f32(a, hi);
-                            st_cluster_f32(a + z_plane_c, lo);
+                            st_cluster_f32(a + P::kPart, lo);
                         }
                     }
                 }
@@ -429,11 +444,12 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                 float y[TDE_MAX_OUT];
 #pragma unroll
                 for (int o = 0; o < TDE_MAX_OUT; ++o) y[o] = 0.0f;
-                const uint32_t cbase = (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u;
+                const int sub = col / NS, cs = col - sub * NS;       // sub-tile, column inside it
+                const uint32_t cbase = (uint32_t)sub * P::kSub + (uint32_t)(cs >> 3) * 1024u + (uint32_t)(cs & 7) * 128u;
                 for (int kg = 0; kg < W / 4; ++kg) {
-                    const uint32_t o4 = (uint32_t)(kg >> 3) * ATOMK + cbase + ((((uint32_t)kg & 7u) ^ (uint32_t)(col & 7)) << 4);
-                    const float4 a = *reinterpret_cast<const float4*>(zhi + o4);
-                    const float4 b = *reinterpret_cast<const float4*>(zlo + o4);
+                    const uint32_t o4 = (uint32_t)(kg >> 3) * P::kAtom + cbase + ((((uint32_t)kg & 7u) ^ (uint32_t)(cs & 7)) << 4);
+                    const float4 a = *reinterpret_cast<const float4*>(zpl + o4);
+                    const float4 b = *reinterpret_cast<const float4*>(zpl + o4 + P::kPart);
                     const float zz[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
 #pragma unroll
                     for (int o = 0; o < TDE_MAX_OUT; ++o)
@@ -473,17 +489,16 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
     constexpr int W = 256;
     constexpr int J = S::J;
     constexpr int NT = kTcPoints * J;
-    constexpr int N2 = 2 * NT;
-    constexpr uint32_t ATOMK = (NT / 8) * 1024;
-    constexpr int kAccSets = tc_acc_sets(1, N2);
-    constexpr uint32_t z_plane_c = (uint32_t)(W / 32) * ATOMK;
+    constexpr int NS = 8 * J;
+    using P = PairPlanes<J>;
+    static_assert(12 * NS <= 512, "two sub-tile regions of 6 x 8J TMEM columns");
+    constexpr int kAccSets = 3;                  // main | hi*lo | lo*hi
     constexpr int n_epi = 512;
     extern __shared__ __align__(1024) unsigned char smem_tc[];
     unsigned char* const smem_raw = smem_tc;
     PairBars* bars = reinterpret_cast<PairBars*>(smem_raw);
-    unsigned char* zhi = smem_raw + 1024;
-    unsigned char* zlo = zhi + z_plane_c;
-    unsigned char* wst = zlo + z_plane_c;
+    unsigned char* zpl = smem_raw + 1024;            // planes, see PairPlanes
+    unsigned char* wst = zpl + P::kBytes;
     const int n_stages = p.n_stages;
     float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * kPairChunkBytes);   // [n_out][W]
     float* xs = wout_s + p.n_out * W;                       // [32][d_in]
@@ -512,13 +527,11 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
             uint32_t ph = 0, act_ph = 0;
             if (crank == 0) {
                 const bool leader = elect_one();
-                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-                const uint64_t b_hi0 = umma_desc_sw128(smem_u32(zhi), 1024);
-                const uint64_t b_lo0 = umma_desc_sw128(smem_u32(zlo), 1024);
+                const uint64_t b0 = umma_desc_sw128(smem_u32(zpl), 1024);
                 const uint64_t a0 = umma_desc(smem_u32(wst), 2048, 128);
                 for (int64_t quad = first_quad; quad < n_quads; quad += quad_step)
                     for (int l = p.L - 1; l >= 1; --l)
-                        pair_issue_layer<N2, NT, kAccSets>(leader, tmem_base, idesc, a0, b_hi0, b_lo0, bars, n_stages, s, ph, act_ph, (uint16_t)(3u << pbase));
+                        pair_issue_layer<J>(leader, tmem_base, a0, b0, bars, n_stages, s, ph, act_ph, (uint16_t)(3u << pbase));
             } else {
                 const uint32_t leader_peer_full0 = mapa_u32(smem_u32(&bars->peer_full[0]), pbase);
                 for (int64_t quad = first_quad; quad < n_quads; quad += quad_step)
@@ -537,10 +550,10 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
         auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(n_epi) : "memory"); };
 
         for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
-        const uint32_t zrow = (uint32_t)(n >> 5) * ATOMK + (uint32_t)(n & 3) * 4u;
+        const uint32_t zrow = (uint32_t)(n >> 5) * P::kAtom + (uint32_t)ph8 * P::kSub + (uint32_t)(n & 3) * 4u;   // k-atom, sub-tile, hi part
         const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;
-        const uint32_t zhi_dest = mapa_u32(smem_u32(zhi), pbase + dest);
-        const uint32_t act_ready_leader = mapa_u32(smem_u32(&bars->act_ready), pbase);
+        const uint32_t zhi_dest = mapa_u32(smem_u32(zpl), pbase + dest);
+        const uint32_t act_ready_leader = mapa_u32(smem_u32(&bars->act_ready[ph8]), pbase);
         // both CTAs of a pair add into the pair's slab (disjoint neurons); the four threads of a neuron (one per group of 8
         // points) into four copies of the small sections, which the reduction sums in a fixed order
         float* gp = p.gpart + (size_t)(blockIdx.x >> 1) * p.gp_stride;
@@ -579,7 +592,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
                 uint32_t zaddr[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    zaddr[j] = zhi_dest + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph8 * (uint32_t)(J * 1024);
+                    zaddr[j] = zhi_dest + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u;
                 const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && pq == 0 && quad == first_quad + 3 * quad_step && l >= 3 && l <= 5;
                 long long* const dst = p.dbg_buf + 16 + ((5 - l) * 2) * 4;
                 if (stamp) dst[0] = clock64();
@@ -588,10 +601,10 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
                 for (int i = 0; i < GC; ++i) st_next[i] = __ldcs(srow_h + (size_t)i * W);
                 uint32_t taddr = 0;
                 if (!last) {
-                    mbar_wait_park(&bars->acc_ready, acc_ph);
+                    mbar_wait_park(&bars->acc_ready[ph8], acc_ph);
                     acc_ph ^= 1;
                     tc_fence_after();
-                    taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(pq * 2 * GC);
+                    taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ph8 * 6 * NS);     // my sub-tile's TMEM region
                 }
                 if (stamp) dst[1] = clock64();
                 float db = 0.0f;
@@ -617,7 +630,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
                     if (!last) {
                         float cur[kAccSets][GC];
 #pragma unroll
-                        for (int a = 0; a < kAccSets; ++a) tmem_ld_cols<GC>(taddr + (uint32_t)(a * N2 + g2 * GC), cur[a]);
+                        for (int a = 0; a < kAccSets; ++a)      // main, hi*lo, lo*hi of my 8 points (owner CTA `dest`)
+                            tmem_ld_cols<GC>(taddr + (a < 2 ? dest * 2 * NS + a * NS : 4 * NS + dest * NS) + (uint32_t)(g2 * GC), cur[a]);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int i = 0; i < GC; ++i) {
@@ -664,7 +678,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_backward_pair_kernel(cons
                                 split_tf32(hb[c], hi, lo);
                                 const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
                                 st_cluster_f32(a, hi);
-                                st_cluster_f32(a + z_plane_c, lo);
+                                st_cluster_f32(a + P::kPart, lo);
                             }
                         } else {
                             // input layer: h = W0 x + b0, h_a = W0[:, first_in[a]]

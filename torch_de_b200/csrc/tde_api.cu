@@ -270,7 +270,7 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         // W = 128: single-CTA kernels, N = 16 J columns per MMA.  W = 256: CTA-pair kernels (cta_group::2), N = 32 J <= 256.
         // TDE_TC_PAIR=1 (W = 256, N = 32 J <= 256): CTA-pair kernels (cta_group::2) instead of the single-CTA ones
         const char* pair_env = getenv("TDE_TC_PAIR");
-        g.use_pair = g.W == 256 && 2 * Ntc <= 256 && pair_env && pair_env[0] == '1';
+        g.use_pair = g.W == 256 && 6 * Ntc <= 512 && pair_env && pair_env[0] == '1';
         const bool shape_ok = (g.W == 128 || g.W == 256) && (g.use_pair || tde::tc_shape_ok(mb, Ntc));
         if (shape_ok && L >= 2 && g.TP % tde::kTcPoints == 0 && !(no_tc && no_tc[0] == '1')) {
             const int64_t atomk = (Ntc / 8) * 1024;
