@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
     float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
     float* xs = wout_s + p.n_out * W;            // [16][d_in]
     float* ybuf = xs + kTcPoints * p.d_in;       // [J*n_out][16]
+    float* bout_s = ybuf + J * p.n_out * kTcPoints; // [n_out]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int n_epi_warps = 8 * MB;
@@ -435,6 +436,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
             auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory"); };
 
             for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
+            if (et < p.n_out) bout_s[et] = p.b_out[et];
             // byte offset of element (col, k = n) inside a Z plane
             const uint32_t hoff = P::template hi_off<kAccSets>((uint32_t)n >> 5);
             const uint32_t zrow = (uint32_t)(n >> 5) * P::kAtom + hoff + (uint32_t)(n & 3) * 4u;   // k-atom, hi part, byte within the 16 B chunk
@@ -572,15 +574,17 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                 epi_sync();   // every neuron's last-layer z is in the planes
                 if (tstamp) p.dbg_buf[42] = clock64();      // last layer's epilogue done everywhere
 
-                // ---- output layer: kOutParts lanes per jet column split the K = W reduction, z = hi + lo ----
-                constexpr int kOutParts = N * 8 <= n_epi ? 8 : (N * 4 <= n_epi ? 4 : (N * 2 <= n_epi ? 2 : 1));
-                if (et < N * kOutParts) {
-                    const int col = et / kOutParts, part = et % kOutParts;
+                // ---- output layer, z = hi + lo: a warp takes 8 jet columns, its four 8-lane groups split the K = W reduction.
+                // 8 lanes reading the same 16 B k-chunk of 8 different columns hit 8 different bank groups (that is what the
+                // 128 B swizzle is for); the first version (4 consecutive lanes per column) was 4-way bank-conflicted: 5 k of the
+                // 8 k cycles this step took with the tensor pipe idle.
+                for (int cw = e; cw < N / 8; cw += n_epi_warps) {       // whole warps: the shuffles below need all 32 lanes
+                    const int col = cw * 8 + (lane & 7), part = lane >> 3;
                     float y[TDE_MAX_OUT];
 #pragma unroll
                     for (int o = 0; o < TDE_MAX_OUT; ++o) y[o] = 0.0f;
                     const uint32_t cbase = (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u;
-                    for (int kg = part; kg < W / 4; kg += kOutParts) {
+                    for (int kg = part; kg < W / 4; kg += 4) {
                         const uint32_t ho = P::template hi_off<kAccSets>((uint32_t)kg >> 3);
                         const uint32_t o4 = (uint32_t)(kg >> 3) * P::kAtom + cbase + ((((uint32_t)kg & 7u) ^ (uint32_t)(col & 7)) << 4);
                         const float4 a = *reinterpret_cast<const float4*>(zpl + o4 + ho);
@@ -589,19 +593,20 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
 #pragma unroll
                         for (int o = 0; o < TDE_MAX_OUT; ++o)
                             if (o < p.n_out) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) y[o] = fmaf(zz[i], wout_s[o * W + kg * 4 + i], y[o]);
+                                const float4 w4 = *reinterpret_cast<const float4*>(wout_s + o * W + kg * 4);
+                                y[o] = fmaf(zz[0], w4.x, fmaf(zz[1], w4.y, fmaf(zz[2], w4.z, fmaf(zz[3], w4.w, y[o]))));
                             }
                     }
 #pragma unroll
-                    for (int o = 0; o < TDE_MAX_OUT; ++o)
-#pragma unroll
-                        for (int d = 1; d < kOutParts; d <<= 1) y[o] += __shfl_xor_sync(0xffffffffu, y[o], d);
+                    for (int o = 0; o < TDE_MAX_OUT; ++o) {
+                        y[o] += __shfl_xor_sync(0xffffffffu, y[o], 8);
+                        y[o] += __shfl_xor_sync(0xffffffffu, y[o], 16);
+                    }
                     if (part == 0) {
                         const int pt = col / J, c = col - pt * J;
 #pragma unroll
                         for (int o = 0; o < TDE_MAX_OUT; ++o)
-                            if (o < p.n_out) ybuf[(c * p.n_out + o) * kTcPoints + pt] = y[o] + (c == 0 ? __ldg(p.b_out + o) : 0.0f);
+                            if (o < p.n_out) ybuf[(c * p.n_out + o) * kTcPoints + pt] = y[o] + (c == 0 ? bout_s[o] : 0.0f);
                     }
                 }
                 epi_sync();

@@ -275,7 +275,7 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         if (shape_ok && L >= 2 && g.TP % tde::kTcPoints == 0 && !(no_tc && no_tc[0] == '1')) {
             const int64_t atomk = (Ntc / 8) * 1024;
             const int pts = g.use_pair ? 2 * tde::kTcPoints : tde::kTcPoints;     // points staged per CTA (x, seeds)
-            const int64_t fixed = 1024 + 2 * (g.W / 32) * atomk + 4 * ((int64_t)g.n_out * g.W + pts * g.d_in + (int64_t)g.J * g.n_out * pts);
+            const int64_t fixed = 1024 + 2 * (g.W / 32) * atomk + 4 * ((int64_t)g.n_out * g.W + pts * g.d_in + (int64_t)g.J * g.n_out * pts + 8);
             const int64_t chunk = g.use_pair ? tde::kPairChunkBytes : (int64_t)mb * 2 * 2 * 2048;
             for (int st = tde::kTcMaxStages; st >= 2; --st)
                 if (fixed + st * chunk <= kSmemLimit) {
