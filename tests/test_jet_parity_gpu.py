@@ -307,6 +307,27 @@ def test_tensor_core_and_ffma_paths_agree(monkeypatch):
     assert rel_l2(g0, g1) < 1e-5
 
 
+def test_cta_pair_kernels_match_reference_and_single_cta(monkeypatch):
+    """TDE_TC_PAIR=1 routes W = 256 through the cta_group::2 kernels (csrc/jet_pair_tc.cuh): same parity bar against the
+    reference's float64 run, and agreement with the default single-CTA kernels."""
+    z, owl, params, groups = load('ldc')
+    res = {}
+    for pair in ('0', '1'):
+        monkeypatch.setenv('TDE_TC_PAIR', pair)
+        res[pair] = run_product('ldc')
+    for k in res['1'][4].derivatives:
+        a, b = res['1'][5]['all'][k].detach().cpu(), res['0'][5]['all'][k].detach().cpu()
+        assert rel_l2(a, b) < TOL_STREAM
+        assert rel_l2(a, z['s64_' + k]) < TOL_STREAM, (k, rel_l2(a, z['s64_' + k]))
+    g1 = torch.cat([g.flatten() for g in res['1'][8]])
+    g0 = torch.cat([g.flatten() for g in res['0'][8]])
+    assert rel_l2(g1, g0) < 1e-5
+    # and it is bitwise repeatable (slab copies per thread, fixed-order reduction)
+    again = run_product('ldc')
+    for x, y in zip(res['1'][8], again[8]):
+        assert torch.equal(x, y)
+
+
 def test_tensor_core_recompute_mode(monkeypatch):
     from torch_de_b200 import engine as E
     grads = {}
