@@ -59,19 +59,21 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
     constexpr int MB = W / 128;
     constexpr int kAccSets = tc_acc_sets(MB, N);
     const int n_stages = p.n_stages;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* empty = full + kTcMaxStages;
-    uint64_t* act_ready = empty + kTcMaxStages;
-    uint64_t* acc_ready = act_ready + 2;     // [neuron block]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
     using P = TcPlanes<N>;
-    unsigned char* zpl = smem_raw + 1024;                   // Hbar planes: [k-atom][hi | lo part][column group][8 x 128 B]
+    unsigned char* zpl = smem_raw;                          // Hbar planes: [k-atom][hi | lo part][column group][8 x 128 B]
     constexpr uint32_t z_planes = (uint32_t)(W / 32) * P::kAtom;
     const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;
     unsigned char* wst = zpl + z_planes;
     float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
     float* xs = wout_s + p.n_out * W;                 // [16][d_in]
-    float* seeds_s = xs + kTcPoints * p.d_in;         // [J*n_out][16]
+    float* seeds_s = xs + kTcPoints * p.d_in;         // [16 points][J channels][4 outputs (padded)]: one float4 per point and channel
+    static_assert(TDE_MAX_OUT == 4, "seed rows are staged as float4 per channel");
+    // barriers at the tail (same carve-up as the forward kernel: [planes][stages][w_out][x][seeds | y][4 floats][barriers])
+    uint64_t* full = reinterpret_cast<uint64_t*>(seeds_s + J * TDE_MAX_OUT * kTcPoints + 4);
+    uint64_t* empty = full + kTcMaxStages;
+    uint64_t* act_ready = empty + kTcMaxStages;
+    uint64_t* acc_ready = act_ready + 2;     // [neuron block]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int n_epi_warps = 8 * MB;
@@ -171,10 +173,11 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     const int64_t gpt = pbase + i / p.d_in;
                     xs[i] = gpt < p.B ? p.x[gpt * p.d_in + (i % p.d_in)] : 0.0f;
                 }
-                for (int i = et; i < J * p.n_out * kTcPoints; i += n_epi) {
-                    const int r = i / kTcPoints, pt = i - r * kTcPoints;
+                for (int i = et; i < J * TDE_MAX_OUT * kTcPoints; i += n_epi) {       // coalesced over the 16 points of a seed row
+                    const int r = i / kTcPoints, pt = i - r * kTcPoints;          // r = channel * 4 + output
+                    const int c = r >> 2, o = r & 3;
                     const int64_t gpt = pbase + pt;
-                    seeds_s[i] = gpt < p.B ? p.seeds[(size_t)r * p.ld_seeds + gpt] : 0.0f;
+                    seeds_s[(pt * J + c) * 4 + o] = (o < p.n_out && gpt < p.B) ? p.seeds[(size_t)(c * p.n_out + o) * p.ld_seeds + gpt] : 0.0f;
                 }
                 epi_sync();
                 if (tstamp) p.dbg_buf[41] = clock64();      // inputs staged
@@ -221,13 +224,15 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     }
                     if (stamp) dst[1] = clock64();
                     float db = 0.0f;
-                    float dwo[TDE_MAX_OUT], dw_in[TDE_MAX_IN];
+                    float dwo[TDE_MAX_OUT], dw_in[TDE_MAX_IN], dh_first[NF > 0 ? NF : 1];
+#pragma unroll
+                    for (int a = 0; a < (NF > 0 ? NF : 1); ++a) dh_first[a] = 0.0f;
 #pragma unroll
                     for (int o = 0; o < TDE_MAX_OUT; ++o) dwo[o] = 0.0f;
 #pragma unroll
                     for (int i = 0; i < TDE_MAX_IN; ++i) dw_in[i] = 0.0f;
                     const float* xs_h = xs + ph * 8 * p.d_in;
-                    const float* seeds_h = seeds_s + ph * 8;
+                    const float4* seeds_h = reinterpret_cast<const float4*>(seeds_s) + ph * 8 * J;     // [point][channel]
                     {
                         asm volatile("" : "+l"(srow_h), "+l"(hrow_h));
 #pragma unroll
@@ -255,14 +260,12 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                                 float st[J], zb[J], hb[J], z[J];
 #pragma unroll
                                 for (int c = 0; c < J; ++c) st[c] = stg[q * J + c];
+                                float4 sd[last ? J : 1];       // seeds of this point: [channel] x 4 outputs (0 beyond n_out)
                                 if (last) {
 #pragma unroll
                                     for (int c = 0; c < J; ++c) {
-                                        float a = 0.0f;
-#pragma unroll
-                                        for (int o = 0; o < TDE_MAX_OUT; ++o)
-                                            if (o < p.n_out) a = fmaf(wo[o], seeds_h[(c * p.n_out + o) * kTcPoints + pt8], a);
-                                        zb[c] = a;
+                                        sd[c] = seeds_h[pt8 * J + c];
+                                        zb[c] = fmaf(wo[0], sd[c].x, fmaf(wo[1], sd[c].y, fmaf(wo[2], sd[c].z, wo[3] * sd[c].w)));
                                     }
                                 } else {
 #pragma unroll
@@ -272,10 +275,12 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                                 db += hb[0];
                                 if (last) {
 #pragma unroll
-                                    for (int c = 0; c < J; ++c)
-#pragma unroll
-                                        for (int o = 0; o < TDE_MAX_OUT; ++o)
-                                            if (o < p.n_out) dwo[o] = fmaf(seeds_h[(c * p.n_out + o) * kTcPoints + pt8], z[c], dwo[o]);
+                                    for (int c = 0; c < J; ++c) {
+                                        dwo[0] = fmaf(sd[c].x, z[c], dwo[0]);
+                                        dwo[1] = fmaf(sd[c].y, z[c], dwo[1]);
+                                        dwo[2] = fmaf(sd[c].z, z[c], dwo[2]);
+                                        dwo[3] = fmaf(sd[c].w, z[c], dwo[3]);
+                                    }
                                 }
                                 if constexpr (KIND >= 1) {
 #pragma unroll
@@ -295,11 +300,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                                     for (int i = 0; i < TDE_MAX_IN; ++i)
                                         if (i < p.d_in) dw_in[i] = fmaf(h0, xs_h[pt8 * p.d_in + i], dw_in[i]);
 #pragma unroll
-                                    for (int a = 0; a < NF; ++a) {
-#pragma unroll
-                                        for (int i = 0; i < TDE_MAX_IN; ++i)
-                                            if (i == p.first_in[a]) dw_in[i] += hb[1 + a];
-                                    }
+                                    for (int a = 0; a < NF; ++a) dh_first[a] += hb[1 + a];     // d/dW0[n][first_in[a]], added once below
                                 }
                             }
                         }
@@ -315,6 +316,11 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     } else {
                         slab_add(gp_lo + p.gp_off_b_in + n, db, first);
 #pragma unroll
+                        for (int a = 0; a < NF; ++a)
+#pragma unroll
+                            for (int i = 0; i < TDE_MAX_IN; ++i)
+                                if (i == p.first_in[a]) dw_in[i] += dh_first[a];
+#pragma unroll
                         for (int i = 0; i < TDE_MAX_IN; ++i)
                             if (i < p.d_in) slab_add(gp_lo + (size_t)n * p.d_in + i, dw_in[i], first);
                     }
@@ -325,11 +331,16 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     }
                 };
                 layer_body(std::integral_constant<int, 2>{}, p.L - 1);
-                for (int l = p.L - 2; l >= 1; --l) layer_body(std::integral_constant<int, 1>{}, l);
+                if (tstamp) p.dbg_buf[45] = clock64();      // last hidden layer's adjoint (from the seeds) published
+                for (int l = p.L - 2; l >= 1; --l) {
+                    layer_body(std::integral_constant<int, 1>{}, l);
+                    if (tstamp && l <= 2) p.dbg_buf[45 + l] = clock64();     // [46]: layer 1 done, [47]: layer 2 done
+                }
                 layer_body(std::integral_constant<int, 0>{}, 0);
+                if (tstamp) p.dbg_buf[48] = clock64();      // input layer done
                 if (et < p.n_out) {
                     float s = 0.0f;
-                    for (int pt = 0; pt < kTcPoints; ++pt) s += seeds_s[(size_t)et * kTcPoints + pt];   // channel-0 rows come first
+                    for (int pt = 0; pt < kTcPoints; ++pt) s += seeds_s[(pt * J) * 4 + et];   // channel 0, output et
                     slab_add(gp + p.gp_off_b_out + et, s, first);
                 }
                 epi_sync();   // xs / seeds_s are rewritten by the next tile

@@ -19,7 +19,8 @@ namespace tde {
 
 constexpr int kTcPoints = 16;      // points per tile
 constexpr int kTcKC = 8;           // k rows per weight chunk (= one tf32 MMA K step)
-constexpr int kTcMaxStages = 8;   // weight stages of the tensor-core kernels (as many as shared memory allows)
+constexpr int kTcMaxStages = 8;
+constexpr int kTcTailBytes = 4 * 4 + (2 * kTcMaxStages + 4) * 8 + 16;   // b_out copy, barriers, TMEM slot   // weight stages of the tensor-core kernels (as many as shared memory allows)
 // 4 control warps + 8 epilogue warps per 128-neuron block: a warp may only read the TMEM lanes 32*(warp%4)..+31, so every
 // lane quarter gets two warps, one per half of the tile's 16 points
 __host__ __device__ constexpr int tc_threads(int W) { return 128 + 256 * (W / 128); }
@@ -336,20 +337,21 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
     constexpr int MB = W / 128;
     constexpr int kAccSets = tc_acc_sets(MB, N);
     const int n_stages = p.n_stages;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* empty = full + kTcMaxStages;
-    uint64_t* act_ready = empty + kTcMaxStages;
-    uint64_t* acc_ready = act_ready + 2;     // [neuron block]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
     using P = TcPlanes<N>;
-    unsigned char* zpl = smem_raw + 1024;                            // activation planes: [k-atom][hi | lo part][column group][8 x 128 B]
+    unsigned char* zpl = smem_raw;                                   // activation planes: [k-atom][hi | lo part][column group][8 x 128 B]
     constexpr uint32_t z_planes = (uint32_t)(W / 32) * P::kAtom;
     const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;   // [hi|lo][mb][kgroup 2][16 row groups][8][4] floats*4
     unsigned char* wst = zpl + z_planes;                             // [n_stages][chunk_bytes]
     float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
     float* xs = wout_s + p.n_out * W;            // [16][d_in]
     float* ybuf = xs + kTcPoints * p.d_in;       // [J*n_out][16]
-    float* bout_s = ybuf + J * p.n_out * kTcPoints; // [n_out]
+    float* bout_s = ybuf + J * TDE_MAX_OUT * kTcPoints; // [4]
+    // barriers at the tail (kTcTailBytes): the planes need the 1024 B alignment of the base, a header would waste ~850 B
+    uint64_t* full = reinterpret_cast<uint64_t*>(bout_s + 4);
+    uint64_t* empty = full + kTcMaxStages;
+    uint64_t* act_ready = empty + kTcMaxStages;
+    uint64_t* acc_ready = act_ready + 2;     // [neuron block]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int n_epi_warps = 8 * MB;

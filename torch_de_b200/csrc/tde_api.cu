@@ -275,7 +275,9 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         if (shape_ok && L >= 2 && g.TP % tde::kTcPoints == 0 && !(no_tc && no_tc[0] == '1')) {
             const int64_t atomk = (Ntc / 8) * 1024;
             const int pts = g.use_pair ? 2 * tde::kTcPoints : tde::kTcPoints;     // points staged per CTA (x, seeds)
-            const int64_t fixed = 1024 + 2 * (g.W / 32) * atomk + 4 * ((int64_t)g.n_out * g.W + pts * g.d_in + (int64_t)g.J * g.n_out * pts + 8);
+            // [planes][weight stages][w_out][x][seeds | y, 4 (padded) outputs per channel][tail: barriers]; the pair kernels keep a 1 KB header
+            const int64_t fixed = (g.use_pair ? 1024 : tde::kTcTailBytes) + 2 * (g.W / 32) * atomk +
+                                  4 * ((int64_t)g.n_out * g.W + pts * g.d_in + (int64_t)g.J * 4 * pts);
             const int64_t chunk = g.use_pair ? tde::kPairChunkBytes : (int64_t)mb * 2 * 2 * 2048;
             for (int st = tde::kTcMaxStages; st >= 2; --st)
                 if (fixed + st * chunk <= kSmemLimit) {
@@ -859,7 +861,8 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
                     fprintf(stderr, "[tc dbg] bwd layer %d block %d: start %lld  acc_ready %lld  body_end %lld  published %lld\n", 5 - l, b,
                             d[0] - h[16], d[1] - h[16], d[2] - h[16], d[3] - h[16]);
                 }
-            fprintf(stderr, "[tc dbg] bwd tile: inputs staged %lld  tile done %lld | layer-5 start %lld\n", h[41] - h[40], h[44] - h[40], h[16] - h[40]);
+            fprintf(stderr, "[tc dbg] bwd tile: inputs staged %lld  last-layer adjoint %lld  layer-5 start %lld | layer 2 done %lld  layer 1 done %lld  input layer done %lld  tile done %lld\n",
+                    h[41] - h[40], h[45] - h[40], h[16] - h[40], h[47] - h[40], h[46] - h[40], h[48] - h[40], h[44] - h[40]);
         }
         {
             ScopedTimer timer(st, 2);
