@@ -31,7 +31,6 @@ struct TcBwdParams {
     int64_t ld_seeds;
     const float* stash;         // forward stash (t | h_c)   [L][bw tiles][cols][W]
     float* hbar;                // Hbar_l                    same layout (layers 1..L-1 used)
-    float* zst;                 // Z_l                       same layout (layers 0..L-2 used)
     int64_t stash_layer_stride;
     int tiles_per_bw_tile;
     float* gpart;               // per-CTA slabs
@@ -360,32 +359,41 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kDwThreads = 640;       // warp 0: stream producer, warp 1: MMA issuer, warps 4..11: Hbar splitters + flushers, warps 12..19: Z splitters
 constexpr int kDwStages = 4;          // operand stages (hi/lo split, UMMA core-matrix order), one 8-column k-step each
-constexpr int kDwRaw = 5;             // raw FP32 stages filled by cp.async.bulk: 8 columns x W neurons of Hbar and of Z
+// raw FP32 stages filled by cp.async.bulk: 8 columns x W neurons of Hbar and of the stash.  The stash side turns 8 points
+// (J k-steps) at a time into post-activation jets, so the ring must hold at least J stages.
+__host__ __device__ constexpr int dw_raw_stages(int J) { return J > 5 ? J : 5; }
 constexpr int kDwFlushTiles = 24;     // accumulator is flushed to the slab after this many 16-point tiles (720 accumulations per chain)
 
 struct TcDwParams {
     int64_t n_tiles;                  // 16-point tiles
     int L, W, MB, J;
     const float* hbar;                // [L][tile][cols][W]
-    const float* zst;
+    const float* stash;               // forward stash (t | h_c), same layout: Z_{l-1} is recomputed from it
+    int act, fourier_half;
     int64_t stash_layer_stride;
     int tiles_per_bw_tile;
     float* gpart;                     // per-CTA slabs; hidden dW of layer l at gp_off_hidden + (l-1)*W*W, [n][k]
     int64_t gp_stride, gp_off_hidden;
 };
 
+// The forward pass keeps only the stash (t | h_c); the post-activation jets Z_{l-1} this GEMM contracts with are recomputed
+// here by the splitter threads of the stash side (a few FMAs per point and neuron; writing them out in the forward and reading
+// them back cost 21 GB of HBM traffic each way and half of the stash memory).
 // Data path: one producer thread streams the two FP32 streams with cp.async.bulk (8 columns = one contiguous 8*W*4 B segment
 // per stream and k-step) into a ring of raw stages.  (Register-buffered loads by the splitter threads were latency-bound: a
 // warp has only six scoreboards, so waiting for the oldest of six load groups also waited for the newest.)  One splitter
 // thread per neuron and stream reads its 8 values from the raw stage, splits them 3xTF32 and writes them as K-major UMMA core
 // matrices into the operand ring.
-template <int UNUSED>
+template <int NF, int SMASK>
 __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_constant__ TcDwParams p) {
+    using S = JetSpecT<NF, SMASK>;
+    constexpr int J = S::J;
+    constexpr int kDwRaw = dw_raw_stages(J);
     extern __shared__ __align__(1024) unsigned char smem_tc[];
     unsigned char* const smem_raw = smem_tc;
     const int W = p.W, MB = p.MB;
-    const int N = 16 * p.J;                       // jet columns per tile
-    const int n_ks = N / 8;                       // k-steps per tile
+    constexpr int N = 16 * J;                     // jet columns per tile
+    constexpr int n_ks = N / 8;                   // k-steps per tile (2 J)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);       // [kDwStages] splitters -> MMA (count = splitter warps)
     uint64_t* empty = full + kDwStages;                            // MMA -> splitters (tcgen05.commit)
     uint64_t* raw_full = empty + kDwStages;                        // [kDwRaw] producer (complete_tx) -> splitters
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
             uint32_t rph = 0;
             for (int l = 1; l < p.L; ++l) {
                 const float* hsrc = p.hbar + (size_t)l * p.stash_layer_stride;
-                const float* zsrc = p.zst + (size_t)(l - 1) * p.stash_layer_stride;
+                const float* zsrc = p.stash + (size_t)(l - 1) * p.stash_layer_stride;
                 for (int64_t t = 0; t < my_tiles; ++t) {
                     const int64_t tile = blockIdx.x + t * gridDim.x;
                     const size_t base = (size_t)tile * N * W;
@@ -516,11 +524,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                 for (int64_t t0 = 0; t0 < my_tiles; t0 += kDwFlushTiles) {
                     const int64_t t1 = t0 + kDwFlushTiles < my_tiles ? t0 + kDwFlushTiles : my_tiles;
                     const int total = (int)(t1 - t0) * n_ks;
-                    for (int j = 0; j < total; ++j) {
-                        // my 8 values of this k-step from the raw stage
+                    auto read_raw = [&](float (&h8)[8]) {       // my 8 values of the next k-step from the raw stage
                         mbar_wait_park(&raw_full[r], rph);
                         const float* rawp = reinterpret_cast<const float*>(raws + (size_t)r * raw_bytes + (size_t)which * op_bytes) + n;
-                        float h8[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) h8[c] = rawp[c * W];
                         __syncwarp();
@@ -529,7 +535,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                             r = 0;
                             rph ^= 1;
                         }
-                        // split and lay out as operand
+                    };
+                    auto emit = [&](const float (&h8)[8]) {     // split and lay out as operand of the next k-step
                         mbar_wait_park(&empty[s], ph ^ 1);
                         unsigned char* st = stages + (size_t)s * stage_bytes + (size_t)which * 2 * op_bytes;   // A_hi|A_lo or B_hi|B_lo
 #pragma unroll
@@ -549,6 +556,32 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                         if (++s == kDwStages) {
                             s = 0;
                             ph ^= 1;
+                        }
+                    };
+                    if (which == 0) {
+                        for (int j = 0; j < total; ++j) {
+                            float h8[8];
+                            read_raw(h8);
+                            emit(h8);
+                        }
+                    } else {
+                        // stash side: 8 points = 8 J columns = J k-steps at a time: (t | h_c) -> Z jets of layer l-1, neuron n
+                        const int actn = layer_act(p.act, p.fourier_half, l - 1, n);
+                        for (int j = 0; j < total; j += J) {
+                            float v[J][8];
+#pragma unroll
+                            for (int ks = 0; ks < J; ++ks) read_raw(v[ks]);
+#pragma unroll
+                            for (int pt = 0; pt < 8; ++pt) {
+                                float st[J], z[J];
+#pragma unroll
+                                for (int c = 0; c < J; ++c) st[c] = v[(pt * J + c) >> 3][(pt * J + c) & 7];
+                                act_recompute<S>(actn, st, z);
+#pragma unroll
+                                for (int c = 0; c < J; ++c) v[(pt * J + c) >> 3][(pt * J + c) & 7] = z[c];
+                            }
+#pragma unroll
+                            for (int ks = 0; ks < J; ++ks) emit(v[ks]);
                         }
                     }
                     if (which) continue;      // Z splitters do not own TMEM lanes

@@ -53,7 +53,6 @@ struct TcParams {
     float* out;
     int64_t ld_out;
     float* stash;          // [L][tile][16*J columns][W]  (t | h_c), nullptr: no gradient wanted
-    float* zst;            // same layout: post-activation jets Z_l of layers 0..L-2 for the weight-gradient GEMM (or nullptr)
     int64_t stash_layer_stride;
     int tiles_per_bw_tile; // TPbw / 16
 };
@@ -468,10 +467,8 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                 constexpr int GC = kTcGroup * J;          // jet columns per 4-point step
                 auto layer_body = [&](auto first_c, auto stash_c, const int l) {
                     constexpr bool kFirst = decltype(first_c)::value;     // input layer (no GEMM) vs hidden layers
-                    constexpr int kMode = decltype(stash_c)::value;     // 0: no stash, 1: stash, 2: stash + Z stream
-                    constexpr bool kStash = kMode >= 1;
+                    constexpr bool kStash = decltype(stash_c)::value;
                     float* srow_h = kStash ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
-                    float* zrow_h = kMode == 2 ? p.zst + (stash_row - p.stash) + (size_t)l * p.stash_layer_stride : nullptr;
                     uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -499,7 +496,6 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                     if (stamp) dst[1] = clock64();
                     {
                         if constexpr (kStash) asm volatile("" : "+l"(srow_h));
-                        if constexpr (kMode == 2) asm volatile("" : "+l"(zrow_h));
 #pragma unroll
                         for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
 #pragma unroll
@@ -542,8 +538,6 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                                 for (int c = 0; c < J; ++c) {
                                     const int col8 = pt8 * J + c;           // column within this half (compile-time)
                                     if constexpr (kStash) __stcs(srow_h + (size_t)col8 * W, h[c]);      // one 128 B line per warp store
-                                    if constexpr (kMode == 2)      // (the last layer's Z is not needed; writing it anyway keeps the loop branch-free)
-                                        __stcs(zrow_h + (size_t)col8 * W, z[c]);
                                     float hi, lo;
                                     split_tf32(z[c], hi, lo);
                                     const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
@@ -563,15 +557,12 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                     }
                     if (stamp) dst[3] = clock64();
                 };
-                if (stash_row && p.zst) {
-                    layer_body(std::true_type{}, std::integral_constant<int, 2>{}, 0);
-                    for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 2>{}, l);
-                } else if (stash_row) {
-                    layer_body(std::true_type{}, std::integral_constant<int, 1>{}, 0);
-                    for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 1>{}, l);
+                if (stash_row) {
+                    layer_body(std::true_type{}, std::true_type{}, 0);
+                    for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::true_type{}, l);
                 } else {
-                    layer_body(std::true_type{}, std::integral_constant<int, 0>{}, 0);
-                    for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 0>{}, l);
+                    layer_body(std::true_type{}, std::false_type{}, 0);
+                    for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::false_type{}, l);
                 }
                 epi_sync();   // every neuron's last-layer z is in the planes
                 if (tstamp) p.dbg_buf[42] = clock64();      // last layer's epilogue done everywhere

@@ -104,6 +104,24 @@ cudaError_t TDE_CAT(launch_backward_tc_, TDE_NF, _, TDE_SMASK)(const TcBwdParams
     return cudaLaunchKernelEx(&cfg, k, p);
 }
 
+// weight-gradient GEMM (recomputes Z from the stash, so it is compiled per jet spec); J <= 6: its raw ring holds J stages
+template <int NF, int SMASK, bool OK = (JetSpecT<NF, SMASK>::J <= 6)>
+struct DwKernel {
+    static void (*get())(TcDwParams) { return jet_dw_tc_kernel<NF, SMASK>; }
+};
+template <int NF, int SMASK>
+struct DwKernel<NF, SMASK, false> {
+    static void (*get())(TcDwParams) { return nullptr; }
+};
+cudaError_t TDE_CAT(launch_dw_tc_, TDE_NF, _, TDE_SMASK)(const TcDwParams& p, int grid, int smem, cudaStream_t st) {
+    void (*k)(TcDwParams) = DwKernel<TDE_NF, TDE_SMASK>::get();
+    if (!k) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kDwThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
 // how many clusters of the pair kernels can be resident at once (a cluster of 4 must fit inside one GPC, so it can be fewer
 // than SMs / 4); the persistent grid must not exceed it.  Returns 0 when the spec has no pair kernel, -1 on error.
 int TDE_CAT(pair_max_clusters_, TDE_NF, _, TDE_SMASK)(int smem) {

@@ -22,11 +22,13 @@ namespace tde {
 typedef cudaError_t (*JetLauncher)(const JetParams&, int grid, int smem, cudaStream_t);
 typedef cudaError_t (*TcLauncher)(const TcParams&, int grid, int smem, cudaStream_t);
 typedef cudaError_t (*TcBwdLauncher)(const TcBwdParams&, int grid, int smem, cudaStream_t);
+typedef cudaError_t (*TcDwLauncher)(const TcDwParams&, int grid, int smem, cudaStream_t);
 #define TDE_DECL(nf, sm)                                                                  \
     cudaError_t launch_forward_##nf##_##sm(const JetParams&, int, int, cudaStream_t);     \
     cudaError_t launch_backward_##nf##_##sm(const JetParams&, int, int, cudaStream_t);     \
     cudaError_t launch_forward_tc_##nf##_##sm(const TcParams&, int, int, cudaStream_t);   \
     cudaError_t launch_backward_tc_##nf##_##sm(const TcBwdParams&, int, int, cudaStream_t); \
+    cudaError_t launch_dw_tc_##nf##_##sm(const TcDwParams&, int, int, cudaStream_t);        \
     int pair_max_clusters_##nf##_##sm(int smem);
 TDE_SPEC_LIST(TDE_DECL)
 #undef TDE_DECL

@@ -331,10 +331,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
             constexpr int GC = kTcGroup * J;          // jet columns per 4-point step
             auto layer_body = [&](auto first_c, auto stash_c, const int l) {
                 constexpr bool kFirst = decltype(first_c)::value;     // input layer (no GEMM) vs hidden layers
-                constexpr int kMode = decltype(stash_c)::value;     // 0: no stash, 1: stash, 2: stash + Z stream
-                constexpr bool kStash = kMode >= 1;
+                constexpr bool kStash = decltype(stash_c)::value;
                 float* srow_h = kStash ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
-                float* zrow_h = kMode == 2 ? p.zst + (stash_row - p.stash) + (size_t)l * p.stash_layer_stride : nullptr;
                 uint32_t zaddr[8];      // cluster address of (column & 7 == j, k = n) in the destination hi plane
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -361,7 +359,6 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                 const float* xs_h = xs + pq * 8 * p.d_in;
                 if (stamp) dst[1] = clock64();
                 if constexpr (kStash) asm volatile("" : "+l"(srow_h));
-                if constexpr (kMode == 2) asm volatile("" : "+l"(zrow_h));
 #pragma unroll
                 for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
 #pragma unroll
@@ -405,8 +402,6 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                         for (int c = 0; c < J; ++c) {
                             const int col8 = pt8 * J + c;           // column within my 8 points (compile-time)
                             if constexpr (kStash) __stcs(srow_h + (size_t)col8 * W, h[c]);      // one 128 B line per warp store
-                                if constexpr (kMode == 2)      // (the last layer's Z is not needed; writing it anyway keeps the loop branch-free)
-                                    __stcs(zrow_h + (size_t)col8 * W, z[c]);
                             float hi, lo;
                             split_tf32(z[c], hi, lo);
                             const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
@@ -426,15 +421,12 @@ __global__ void __launch_bounds__(kPairThreads, 1) jet_forward_pair_kernel(const
                 }
                 if (stamp) dst[3] = clock64();
             };
-            if (stash_row && p.zst) {
-                layer_body(std::true_type{}, std::integral_constant<int, 2>{}, 0);
-                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 2>{}, l);
-            } else if (stash_row) {
-                layer_body(std::true_type{}, std::integral_constant<int, 1>{}, 0);
-                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 1>{}, l);
+            if (stash_row) {
+                layer_body(std::true_type{}, std::true_type{}, 0);
+                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::true_type{}, l);
             } else {
-                layer_body(std::true_type{}, std::integral_constant<int, 0>{}, 0);
-                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::integral_constant<int, 0>{}, l);
+                layer_body(std::true_type{}, std::false_type{}, 0);
+                for (int l = 1; l < p.L; ++l) layer_body(std::false_type{}, std::false_type{}, l);
             }
             mbar_wait_cluster(&bars->planes_done, tile_ph);   // every neuron's last-layer z of MY tile is in my planes
 

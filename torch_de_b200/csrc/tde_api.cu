@@ -70,9 +70,10 @@ struct Dispatch {
     tde::JetLauncher fwd, bwd;
     tde::TcLauncher fwd_tc;
     tde::TcBwdLauncher bwd_tc;
+    tde::TcDwLauncher dw_tc;
     int (*pair_max_clusters)(int smem);
 };
-#define TDE_ROW(nf, sm) {nf, sm, tde::launch_forward_##nf##_##sm, tde::launch_backward_##nf##_##sm, tde::launch_forward_tc_##nf##_##sm, tde::launch_backward_tc_##nf##_##sm, tde::pair_max_clusters_##nf##_##sm},
+#define TDE_ROW(nf, sm) {nf, sm, tde::launch_forward_##nf##_##sm, tde::launch_backward_##nf##_##sm, tde::launch_forward_tc_##nf##_##sm, tde::launch_backward_tc_##nf##_##sm, tde::launch_dw_tc_##nf##_##sm, tde::pair_max_clusters_##nf##_##sm},
 const Dispatch kDispatch[] = {TDE_SPEC_LIST(TDE_ROW)};
 #undef TDE_ROW
 
@@ -126,7 +127,7 @@ struct Geometry {
     // tcgen05 forward (wide layers)
     int use_tc, use_pair, tc_mb, tc_stages, tc_smem, tc_nacc;
     int use_tc_bwd, dw_smem;
-    int64_t o_wct, o_hbar, o_zst, grid_b1, grid_b2;
+    int64_t o_wct, o_hbar, grid_b1, grid_b2;
     int64_t tc_tiles;
     // per-CTA partial gradient slab
     int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo, gp_stride;
@@ -294,8 +295,8 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.use_tc_bwd = 0;
     {
         const char* no_b = getenv("TDE_NO_TC_BWD");
-        g.dw_smem = 1024 + (tde::kDwStages * 4 + tde::kDwRaw * 2) * g.W * 32;
-        if (g.use_tc && g.dw_smem <= kSmemLimit && !(no_b && no_b[0] == '1')) {
+        g.dw_smem = 1024 + (tde::kDwStages * 4 + tde::dw_raw_stages(g.J) * 2) * g.W * 32;
+        if (g.use_tc && g.J <= 6 && g.dw_smem <= kSmemLimit && !(no_b && no_b[0] == '1')) {
             g.use_tc_bwd = 1;
             g.rsplit = 1;      // the FFMA dW phase (and its column split) is not used on this path
         }
@@ -338,15 +339,11 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.stash_floats = (int64_t)L * g.stash_layer_stride;
     g.stash_total_floats = g.stash_floats;
     g.workspace_floats = align_up(g.packed_floats + (int64_t)std::max(g.n_ctas, sm_count()) * g.gp_stride, 64);
-    g.o_hbar = g.o_zst = 0;
+    g.o_hbar = 0;
     if (g.use_tc_bwd) {       // Hbar_l and Z_l streams for the tensor-core weight-gradient kernel
-        // Hbar_l stream (written by the reverse sweep, read by the weight-gradient GEMM of the same call) lives in the
-        // workspace; the Z_l stream is written by the FORWARD pass and read by the backward pass, so it travels with the
-        // stash (second half of the caller's stash buffer): another forward on the same workspace must not clobber it
+        // Hbar_l stream: written by the reverse sweep, read by the weight-gradient GEMM of the same call
         g.o_hbar = g.workspace_floats;
         g.workspace_floats = g.o_hbar + g.stash_floats;
-        g.o_zst = g.stash_floats;             // offset inside the stash buffer
-        g.stash_total_floats = 2 * g.stash_floats;
         const int cl = g.use_pair ? tde::kPairCluster : tde::kTcCluster;
         const int64_t groups = (g.tc_tiles + cl - 1) / cl;
         g.grid_b1 = cl * std::max<int64_t>(1, std::min<int64_t>(tc_cluster_slots(g.disp, g.use_pair != 0, g.tc_smem), groups));
@@ -775,7 +772,6 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
         t.w_in = ws + g.o_w_in; t.b_in = ws + g.o_b_in; t.wc = ws + g.o_wc; t.b_hidden = ws + g.o_bh;
         t.w_out = ws + g.o_wo; t.b_out = ws + g.o_bo;
         t.out = out; t.ld_out = ld_out; t.stash = stash;
-        t.zst = stash && g.use_tc_bwd ? stash + g.o_zst : nullptr;     // second half of the stash buffer
         t.stash_layer_stride = g.stash_layer_stride;
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
         // clusters of kTcCluster CTAs: even grid, never more clusters than tile pairs
@@ -831,7 +827,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
         t.wct = ws + g.o_wct; t.w_out = ws + g.o_wo;
         t.seeds = seeds; t.ld_seeds = ld_seeds; t.stash = stash;
-        t.hbar = ws + g.o_hbar; t.zst = const_cast<float*>(stash) + g.o_zst;
+        t.hbar = ws + g.o_hbar;
         t.stash_layer_stride = g.stash_layer_stride;
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
         t.gpart = ws + g.o_gpart; t.gp_stride = g.gp_stride;
@@ -839,7 +835,8 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         for (int k = 0; k < 4; ++k) { t.gp_dup_lo[k] = g.g_dup_lo[k]; t.gp_dup_hi[k] = g.g_dup_hi[k]; }
         tde::TcDwParams d{};
         d.n_tiles = g.tc_tiles; d.L = g.L; d.W = g.W; d.MB = g.tc_mb; d.J = g.J;
-        d.hbar = t.hbar; d.zst = t.zst; d.stash_layer_stride = t.stash_layer_stride; d.tiles_per_bw_tile = t.tiles_per_bw_tile;
+        d.hbar = t.hbar; d.stash = stash; d.act = g.act; d.fourier_half = g.fourier_half;
+        d.stash_layer_stride = t.stash_layer_stride; d.tiles_per_bw_tile = t.tiles_per_bw_tile;
         d.gpart = t.gpart; d.gp_stride = g.gp_stride; d.gp_off_hidden = g.g_hidden;
         static long long* bdbg = nullptr;
         const char* dbg_env = getenv("TDE_TC_DBG");
@@ -867,10 +864,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         {
             ScopedTimer timer(st, 2);
             if (g.L >= 2) {
-                auto k = tde::jet_dw_tc_kernel<0>;
-                TDE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g.dw_smem));
-                k<<<(int)g.grid_b2, tde::kDwThreads, g.dw_smem, st>>>(d);
-                TDE_CUDA(cudaGetLastError());
+                TDE_CUDA(g.disp->dw_tc(d, (int)g.grid_b2, g.dw_smem, st));
             }
         }
         g_launches += 3;
