@@ -568,20 +568,28 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                         // stash side: 8 points = 8 J columns = J k-steps at a time: (t | h_c) -> Z jets of layer l-1, neuron n
                         const int actn = layer_act(p.act, p.fourier_half, l - 1, n);
                         for (int j = 0; j < total; j += J) {
+                            // every output k-step is emitted as soon as the points that touch its 8 columns are converted:
+                            // reads, conversions and emits interleave (all indices compile-time) instead of J reads, 8
+                            // conversions, J emits in a row, which starved the MMAs between bursts
                             float v[J][8];
+                            static_for<J>([&](auto ks_c) {
+                                constexpr int ks = decltype(ks_c)::value;
+                                constexpr int prev_pt = ks == 0 ? -1 : (8 * (ks - 1) + 7) / J;      // last point converted so far
+                                constexpr int need_pt = (8 * ks + 7) / J;                            // last point touching k-step ks
+                                constexpr int prev_raw = prev_pt < 0 ? -1 : ((prev_pt + 1) * J - 1) / 8;
+                                constexpr int need_raw = ((need_pt + 1) * J - 1) / 8;                // last raw k-step that point needs
+                                static_for<need_raw - prev_raw>([&](auto i_c) { read_raw(v[prev_raw + 1 + decltype(i_c)::value]); });
+                                static_for<need_pt - prev_pt>([&](auto i_c) {
+                                    constexpr int pt = prev_pt + 1 + decltype(i_c)::value;
+                                    float st[J], z[J];
 #pragma unroll
-                            for (int ks = 0; ks < J; ++ks) read_raw(v[ks]);
+                                    for (int c = 0; c < J; ++c) st[c] = v[(pt * J + c) >> 3][(pt * J + c) & 7];
+                                    act_recompute<S>(actn, st, z);
 #pragma unroll
-                            for (int pt = 0; pt < 8; ++pt) {
-                                float st[J], z[J];
-#pragma unroll
-                                for (int c = 0; c < J; ++c) st[c] = v[(pt * J + c) >> 3][(pt * J + c) & 7];
-                                act_recompute<S>(actn, st, z);
-#pragma unroll
-                                for (int c = 0; c < J; ++c) v[(pt * J + c) >> 3][(pt * J + c) & 7] = z[c];
-                            }
-#pragma unroll
-                            for (int ks = 0; ks < J; ++ks) emit(v[ks]);
+                                    for (int c = 0; c < J; ++c) v[(pt * J + c) >> 3][(pt * J + c) & 7] = z[c];
+                                });
+                                emit(v[ks]);
+                            });
                         }
                     }
                     if (which) continue;      // Z splitters do not own TMEM lanes
