@@ -308,9 +308,9 @@ def run_ours(args, rank, local_rank, world):
         del k["flops"], k["tensor"], k["ms"]
     # DRAM bytes per point measured by `ncu --set full` at this workload (profiles/r01_tc_kernels_ncu_full_summary.csv:
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 510 000 points); other workloads: not captured.
-    traffic_per_point = {"jet_forward_tc_kernel": (0.010091 + 41.753216) * 1e9 / 510000,
-                         "jet_backward_tc_kernel": (20.933042 + 18.381886) * 1e9 / 510000,
-                         "jet_dw_tc_kernel": (38.732598 + 2.425837) * 1e9 / 510000} if args.workload == "ldc" else {}
+    traffic_per_point = {"jet_forward_tc_kernel": (0.009378 + 20.872160) * 1e9 / 510000,
+                         "jet_backward_tc_kernel": (20.940418 + 18.390353) * 1e9 / 510000,
+                         "jet_dw_tc_kernel": (38.728196 + 2.437561) * 1e9 / 510000} if args.workload == "ldc" else {}
     for k in kernels:
         per_pt = traffic_per_point.get(k["kernel"])
         k["traffic"] = per_pt * pts_total / max(1, k["launches"]) if per_pt else None
