@@ -3,13 +3,14 @@
 //
 //   D[neuron][col] = sum_k W_l[neuron][k] * Z[k][col]        col = pt*J + channel, 16 points per CTA tile
 //
-// A operand = weights (M = 128 neurons per block, K-major): streamed by a producer warp with cp.async.bulk from a
-//             global image that is already in UMMA core-matrix order and already split into hi/lo.
-// B operand = activations (N = 16*J jet columns, K-major): resident in shared memory as two planes Z_hi, Z_lo,
-//             written by the epilogue of the previous layer in UMMA core-matrix order (8 cols x 4 k per 128 B).
-// D         = TMEM, lane = neuron => after tcgen05.ld every epilogue thread owns ALL jet channels of its neuron for
-//             every point of the tile, which is exactly what the jet activation needs (no cross-lane exchange).
-// Roles: warp 0 weight producer, warp 1 MMA issuer (one elected thread), warps 4.. epilogue (1 thread per neuron).
+// A operand = weights (M = 128 neurons per block, K-major): streamed by a producer thread with cp.async.bulk (multicast to
+//             the cluster peer) from a global image that is already in UMMA core-matrix order and already split into hi/lo.
+// B operand = activations (N = 16*J jet columns, K-major SWIZZLE_128B): resident in shared memory, hi and lo column groups
+//             side by side per k-atom (see TcPlanes / tc_issue_layer), written by the epilogue of the previous layer.
+// D         = TMEM, lane = neuron => after tcgen05.ld every epilogue thread owns ALL jet channels of its neuron for its
+//             points of the tile, which is exactly what the jet activation needs (no cross-lane exchange).
+// Roles: warp 0 weight producer, warp 1 MMA issuer (one elected thread), warps 4.. epilogue (8 warps per 128-neuron block:
+// one thread per neuron and half of the tile's points).  Shared memory: [planes][weight stages][w_out][x][y][barriers].
 #pragma once
 #include <type_traits>
 #include <utility>
@@ -42,7 +43,7 @@ struct TcParams {
     long long* dbg_buf;    // optional cycle stamps (TDE_TC_DBG bit 2)
     int dbg;               // bit 2: cycle stamps; bit 3: pair kernel without weight streaming (timing experiment only)
     int pair;              // W = 256: use the CTA-pair kernel
-    int n_acc;             // TMEM accumulator sets: 3 = {small terms, main even k-steps, main odd k-steps}, 2, or 1
+    int n_acc;             // informational: TMEM accumulator sets the kernel uses (tc_acc_sets; compile-time in the kernel)
     int first_in[TDE_MAX_FIRST];
     const float* w_in;     // [W][d_in]
     const float* b_in;     // [W]
@@ -54,7 +55,7 @@ struct TcParams {
     int64_t ld_out;
     float* stash;          // [L][tile][16*J columns][W]  (t | h_c), nullptr: no gradient wanted
     int64_t stash_layer_stride;
-    int tiles_per_bw_tile; // TPbw / 16
+    int tiles_per_bw_tile; // FFMA tile / 16 (informational: the stash is addressed by 16-point tile)
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
