@@ -81,3 +81,32 @@ def test_loss_handler_variants():
     assert float(L({'a': ga, 'b': gb}, out, power=1, aggregation_method='sum').grouped_losses('group')['a']) == pytest.approx(6.0 + 3.0)
     with pytest.raises(ValueError):
         loss.grouped_losses('nope')
+
+
+def test_loss_weighting_rules_match_reference_formulas():
+    """GradNorm / Causal_weighting (reference utils/Loss_weighting.py:30-67) on plain torch graphs: the update rules are host
+    logic, independent of the kernels."""
+    import math
+    import torch
+    import torch_de_b200 as T
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(2, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    x = torch.rand(7, 2)
+    u = net(x)
+    losses = [u.pow(2).mean(), 10.0 * (u - 1).pow(2).mean(), u.sum() * 0.0]      # the last one has zero gradient
+    w0 = torch.tensor([1.0, 2.0, 3.0])
+    w = T.GradNorm(net, w0, *losses, alpha=0.5, max_weight=100.0)
+    mags = []
+    for l in losses:
+        g = torch.autograd.grad(l, list(net.parameters()), retain_graph=True, allow_unused=True)
+        mags.append(math.sqrt(sum(float(t.pow(2).sum()) for t in g if t is not None)))
+    total = sum(mags)
+    want = [0.5 * float(w0[k]) + 0.5 * (min(total / mags[k], 100.0) if mags[k] > 1e-5 else float(w0[k])) for k in range(3)]
+    assert torch.allclose(w, torch.tensor(want), rtol=1e-5)
+    # causal weights: exp(-eps * running sum of the mean residual), first weight 1
+    r1, r2 = torch.rand(6), torch.rand(6)
+    cw = T.Causal_weighting({'residual': {'g': {'a': r1, 'b': r2}}}, eps=0.7)
+    mean = (r1 + r2) / 2
+    ref = torch.exp(-0.7 * torch.cumsum(mean, 0))
+    ref[0] = 1
+    assert torch.allclose(cw, ref)
