@@ -178,6 +178,15 @@ int tde_plan_paths(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points);
 /* Measures the sustained scalar-FFMA rate of this GPU (TFLOP/s); the FFMA kernels' roofline denominator. */
 int tde_fp32_peak_probe(double* tflops, void* stream);
 
+/* Bilinear lookup on a regular 2-D grid (signed-distance / point-weight fields), the device replacement of
+ * torch_DE/utils/GridInterpolator.py:50-83 (RegularGridInterpolator.interpolate for two dimensions):
+ *   gx[nx], gy[ny] ascending grid coordinates, values[nx][ny] row-major, x[n], y[n] query coordinates, out[n].
+ * Same conventions as the reference: right index = first grid point >= x (clamped), left = right - 1 (clamped), negative
+ * distances are 0, a query exactly on a grid line whose both distances are 0 gets weights 1/1, outside the grid the edge value
+ * is returned.  All pointers are device pointers. */
+int tde_grid_interp2d(const float* gx, int32_t nx, const float* gy, int32_t ny, const float* values, const float* x, const float* y,
+                      int64_t n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,7 +49,7 @@ class TdeLossProgram(C.Structure):
 
 EXPORTS = ["tde_last_error", "tde_version", "tde_abi_struct_bytes", "tde_plan", "tde_jet_forward", "tde_jet_backward",
            "tde_residual_loss", "tde_adam_step", "tde_fp32_peak_probe", "tde_launch_count", "tde_profile_begin",
-           "tde_profile_end", "tde_profile_kind", "tde_plan_paths"]
+           "tde_profile_end", "tde_profile_kind", "tde_plan_paths", "tde_grid_interp2d"]
 
 _LIB = None
 
@@ -71,6 +71,7 @@ def _declare(lib):
         getattr(lib, name).restype = C.c_int
     lib.tde_profile_kind.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.tde_plan_paths.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), i64]
+    lib.tde_grid_interp2d.argtypes = [vp, i32, vp, i32, vp, vp, vp, i64, vp, vp]
     lib.tde_launch_count.restype = C.c_longlong
     lib.tde_launch_count.argtypes = []
     return lib

@@ -710,6 +710,58 @@ __global__ void __launch_bounds__(512) ffma_probe_kernel(float* out, int iters, 
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// bilinear grid lookup (GridInterpolator.py:50-83), one thread per query point
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <bool SMEM>
+__device__ __forceinline__ float grid_at(const float* g, const int i) { return SMEM ? g[i] : __ldg(g + i); }
+template <bool SMEM>
+__device__ __forceinline__ void grid_bracket(const float* g, const int n, const float x, int& il, int& ir, float& dl, float& dr) {
+    int lo = 0, hi = n;                       // first index with g[i] >= x  (torch.bucketize, right = false)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (grid_at<SMEM>(g, mid) < x) lo = mid + 1; else hi = mid;
+    }
+    ir = lo < n ? lo : n - 1;
+    il = ir - 1 < 0 ? 0 : ir - 1;
+    dl = x - grid_at<SMEM>(g, il);
+    dr = grid_at<SMEM>(g, ir) - x;
+    if (dl < 0.0f) dl = 0.0f;
+    if (dr < 0.0f) dr = 0.0f;
+    if (dl == 0.0f && dr == 0.0f) dl = dr = 1.0f;
+}
+// SMEM: the two coordinate arrays are staged in shared memory (the binary searches are 2 x log2(n) dependent loads per point)
+template <bool SMEM>
+__global__ void grid_interp2d_kernel(const float* __restrict__ gx, const int nx, const float* __restrict__ gy, const int ny,
+                                     const float* __restrict__ values, const float* __restrict__ x, const float* __restrict__ y,
+                                     const int64_t n, float* __restrict__ out) {
+    extern __shared__ float grid_s[];
+    const float* sx = gx;
+    const float* sy = gy;
+    if (SMEM) {
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) grid_s[i] = gx[i];
+        for (int i = threadIdx.x; i < ny; i += blockDim.x) grid_s[nx + i] = gy[i];
+        __syncthreads();
+        sx = grid_s;
+        sy = grid_s + nx;
+    }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int xl, xr, yl, yr;
+        float dxl, dxr, dyl, dyr;
+        grid_bracket<SMEM>(sx, nx, __ldcs(x + i), xl, xr, dxl, dxr);
+        grid_bracket<SMEM>(sy, ny, __ldcs(y + i), yl, yr, dyl, dyr);
+        // corner order and weights as in the reference: value[left/right] * distance to the OTHER side
+        float num = 0.0f;
+        num += __ldg(values + (int64_t)xl * ny + yl) * (dxr * dyr);
+        num += __ldg(values + (int64_t)xl * ny + yr) * (dxr * dyl);
+        num += __ldg(values + (int64_t)xr * ny + yl) * (dxl * dyr);
+        num += __ldg(values + (int64_t)xr * ny + yr) * (dxl * dyl);
+        __stcs(out + i, num / ((dxl + dxr) * (dyl + dyr)));
+    }
+}
+}  // namespace
+
 extern "C" {
 
 const char* tde_last_error(void) { return g_err.c_str(); }
@@ -1004,6 +1056,23 @@ int tde_fp32_peak_probe(double* tflops, void* stream) {
     cudaFree(buf);
     TDE_CUDA(cudaGetLastError());
     *tflops = 2.0 * 16 * iters * (double)threads * grid / (best * 1e-3) * 1e-12;
+    return 0;
+}
+
+int tde_grid_interp2d(const float* gx, int32_t nx, const float* gy, int32_t ny, const float* values, const float* x, const float* y,
+                      int64_t n, float* out, void* stream) {
+    if (n == 0) return 0;
+    if (!gx || !gy || !values || !x || !y || !out) return fail("null pointer");
+    if (nx < 1 || ny < 1 || n < 0) return fail("grid %d x %d, %lld points", nx, ny, (long long)n);
+    const int threads = 512;
+    const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, (int64_t)sm_count() * 4);
+    const size_t smem = (size_t)(nx + ny) * sizeof(float);
+    if (smem <= 40 * 1024)
+        grid_interp2d_kernel<true><<<blocks, threads, smem, (cudaStream_t)stream>>>(gx, nx, gy, ny, values, x, y, n, out);
+    else
+        grid_interp2d_kernel<false><<<blocks, threads, 0, (cudaStream_t)stream>>>(gx, nx, gy, ny, values, x, y, n, out);
+    TDE_CUDA(cudaGetLastError());
+    ++g_launches;
     return 0;
 }
 
