@@ -5,7 +5,7 @@ from .de_getter import DE_Getter
 from .engine import FD_engine, Jet_engine, JetRunner
 from .equations import DE_func, get_derivatives, get_NavierStokes
 from .loss import Loss, Loss_handler
-from .loss_weighting import GradNorm, Causal_weighting
+from .grad_balance import GradNorm, Causal_weighting
 from .point_weights import RegularGridInterpolator, R3_sampler, sample_from_tensor
 from .networks import MLP, Fourier_Embedding, Fourier_Net, RWF_Linear, Sin, extract_layers
 from .spec import JetChannels, derivative_index_map
