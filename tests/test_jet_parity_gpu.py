@@ -473,3 +473,36 @@ def test_gradnorm_weights_follow_reference_rule():
                         for r in rows])
     expect = 0.9 * w0 + 0.1 * (mags.sum() / mags)
     assert torch.allclose(w1, expect, rtol=1e-4)
+
+
+def test_graphed_step_replays_the_eager_step_bitwise():
+    """torch_de_b200.GraphedStep: the whole training step (calculate -> fused losses -> backward -> Adam) captured in one CUDA
+    graph gives bit-identical losses and parameters to the eager step (Burgers 8x64: launch-bound)."""
+    z, owl, params, groups = load('burgers')
+    wl = product_workload('burgers')
+    results = {}
+    for mode in ('eager', 'graph'):
+        net, lins = load_net(wl, params, 'cuda')
+        pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+        batch = T.make_batch(wl.input_vars, {g: x.to('cuda') for g, x in groups.items()})
+        handler = wl.build_losses(list(groups.keys()))
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            out = pinn.calculate(batch)
+            total = wl.combine(handler(batch, out).grouped_losses('loss_type'))
+            total.backward()
+            opt.step()
+            return total
+
+        if mode == 'graph':
+            step = T.GraphedStep(step, warmup=2)           # 2 warm-up steps + 1 captured (not run) ...
+            losses = [float(step()) for _ in range(3)]
+        else:
+            for _ in range(2):
+                step()                                      # ... = the same 2 steps before the 3 compared ones
+            losses = [float(step()) for _ in range(3)]
+        results[mode] = (losses, torch.cat([p.detach().flatten().cpu() for p in net.parameters()]))
+    assert results['eager'][0] == results['graph'][0]
+    assert torch.equal(results['eager'][1], results['graph'][1])
