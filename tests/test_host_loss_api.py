@@ -110,3 +110,13 @@ def test_loss_weighting_rules_match_reference_formulas():
     ref = torch.exp(-0.7 * torch.cumsum(mean, 0))
     ref[0] = 1
     assert torch.allclose(cw, ref)
+
+
+def test_graphed_step_needs_a_device():
+    import pytest
+    import torch
+    import torch_de_b200 as T
+    if torch.cuda.is_available():
+        pytest.skip('covered by the GPU test')
+    with pytest.raises(RuntimeError):
+        T.GraphedStep(lambda: torch.zeros(()))
