@@ -545,11 +545,25 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
     float s = 0.0f;
     const int n_slabs = splits > 1 || src >= a.g_hidden && src < a.g_bh ? a.n_active_hidden : a.n_active;
     const int which = src < a.g_hidden ? 1 : (src >= a.g_bh && src < a.g_bo ? 2 : 0);
-    for (int c = 0; c < n_slabs; ++c) {
-        const float* slab = gpart + (int64_t)c * a.gp_stride + src;
-        for (int q = 0; q < splits; ++q) s += slab[(int64_t)q * WW];
-        if (which)
-            for (int k = 1; k < a.n_copies; ++k) s += slab[which == 1 ? a.dup_lo[k] : a.dup_hi[k]];
+    if (splits == 1 && !(which && a.n_copies > 1)) {
+        // common case (hidden weights on the tensor path): one value per slab.  Eight loads are in flight at a time; the
+        // additions stay in slab order, so the result does not depend on the batching
+        int c = 0;
+        for (; c + 8 <= n_slabs; c += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcs(gpart + (int64_t)(c + u) * a.gp_stride + src);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; c < n_slabs; ++c) s += __ldcs(gpart + (int64_t)c * a.gp_stride + src);
+    } else {
+        for (int c = 0; c < n_slabs; ++c) {
+            const float* slab = gpart + (int64_t)c * a.gp_stride + src;
+            for (int q = 0; q < splits; ++q) s += slab[(int64_t)q * WW];
+            if (which)
+                for (int k = 1; k < a.n_copies; ++k) s += slab[which == 1 ? a.dup_lo[k] : a.dup_hi[k]];
+        }
     }
     flat[i] += a.scale * s;
 }
