@@ -82,10 +82,11 @@ typedef struct TdePlan {
     int32_t n_ctas;           /* persistent grid size */
     int64_t n_tiles;
     int64_t stash_bytes;      /* forward -> backward activation stash (0 if B == 0) */
-    int64_t workspace_bytes;  /* packed weights + per-CTA partial gradients */
+    int64_t workspace_bytes;  /* packed weights + per-CTA partial gradients (+ the Hbar stream of the tensor-core backward) */
     int64_t n_params;         /* floats in the flat gradient, net.parameters() order */
     int32_t smem_forward;
     int32_t smem_backward;
+    int64_t workspace_forward_bytes;  /* what tde_jet_forward alone touches of the workspace (packed weights) */
 } TdePlan;
 
 const char* tde_last_error(void);
@@ -174,6 +175,10 @@ int tde_profile_end(double* forward_ms_total, int32_t* n_forward, double* backwa
 int tde_profile_kind(int kind, double* ms_total, int32_t* n_launches);
 /* which kernels a (net, spec, n_points) call uses: bit0 tcgen05 forward, bit1 tcgen05 reverse sweep + dW GEMM. */
 int tde_plan_paths(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points);
+
+/* Run-time switches for A/B measurements and debugging (the matching TDE_* environment variables are read once, at the first
+ * call into the library): "no_tc", "no_tc_bwd", "tc_pair", "tc_slots", "tc_stages", "tc_dbg". */
+int tde_set_option(const char* name, int value);
 
 /* Measures the sustained scalar-FFMA rate of this GPU (TFLOP/s); the FFMA kernels' roofline denominator. */
 int tde_fp32_peak_probe(double* tflops, void* stream);

@@ -301,25 +301,43 @@ def _ldc(width=256, n_act=8, name='ldc'):
                     rows, lambda s: s['residual'] + 100 * s['boundary'])                # :92-94
 
 
-def _cylinder():
-    lo, hi = [0.0, 0.0], [22.0, 4.1]
+_NS_DERIVS_T = ['u_x', 'u_y', 'u_t', 'u_xx', 'u_yy', 'p_x', 'v_x', 'v_y', 'v_t', 'v_xx', 'v_yy', 'p_y']
+
+
+def _cylinder(width=512, n_act=10, name='cylinder', steady=True, activation='tanh'):
+    """Cylinder-flow box with get_NavierStokes(2, steady_state, Re=100) residuals (Equations/NavierStokes.py:8-80,
+    Tutorials/Stokes_Cylinder.py:21,65-79); the unsteady variant adds t in [0,1], the u_t / v_t terms (NavierStokes.py:9,14)
+    and an initial-condition group with the tutorial's parabolic inlet profile (Stokes_Cylinder.py:64)."""
+    d = 2 if steady else 3
+    lo, hi = [0.0, 0.0] + ([] if steady else [0.0]), [22.0, 4.1] + ([] if steady else [1.0])
 
     def rows(g, x, o):
         if g == 'collocation points':
-            ns_x, ns_y, inc = _ns_rows(o, 100.0)       # get_NavierStokes(2, steady_state=True, Re): NavierStokes.py:8-23
+            ns_x, ns_y, inc = _ns_rows(o, 100.0)
+            if not steady:
+                ns_x, ns_y = o['u_t'] + ns_x, o['v_t'] + ns_y
             return [('residual', 'NavierStokes_x', ns_x, 1.0), ('residual', 'NavierStokes_y', ns_y, 1.0),
                     ('residual', 'incompressible', inc, 1.0)]
         if g == 'inlet':
             return [('boundary', 'u', o['u'] - 1.0, 1.0), ('boundary', 'v', o['v'] - 0.0, 1.0)]
+        if g == 'initial condition':
+            y = x[:, 1]
+            return [('initial condition', 'u', o['u'] - 4 * y * (4.1 - y) / 4.1 ** 2, 1.0), ('initial condition', 'v', o['v'] - 0.0, 1.0)]
         return [('boundary', 'u', o['u'] - 0.0, 1.0), ('boundary', 'v', o['v'] - 0.0, 1.0)]
-    return Workload('cylinder', ['x', 'y'], ['u', 'v', 'p'], _NS_DERIVS, dict(d_in=2, n_out=3, width=512, n_act=10),
-                    [('collocation points', _uniform(lo, hi)),
-                     ('inlet', _edge(0, 0.0, lo, hi)),
-                     ('no slip', _edge(1, 0.0, lo, hi))],
-                    rows, lambda s: s['residual'] + 100 * s['boundary'])
+    groups = [('collocation points', _uniform(lo, hi)), ('inlet', _edge(0, 0.0, lo, hi)), ('no slip', _edge(1, 0.0, lo, hi))]
+    if not steady:
+        groups.append(('initial condition', _edge(2, 0.0, lo, hi)))
+    return Workload(name, ['x', 'y'] + ([] if steady else ['t']), ['u', 'v', 'p'], _NS_DERIVS if steady else _NS_DERIVS_T,
+                    dict(d_in=d, n_out=3, width=width, n_act=n_act), groups, rows,
+                    lambda s: s['residual'] + 100 * s['boundary'] + (0 if steady else 100 * s['initial condition']), activation)
 
 
-WORKLOADS = {'spring': _spring, 'burgers': _burgers, 'allen_cahn': _allen_cahn, 'ldc': _ldc, 'cylinder': _cylinder}
+def _cylinder_unsteady(width=512, n_act=10, name='cylinder_unsteady', activation='tanh'):
+    return _cylinder(width, n_act, name, steady=False, activation=activation)
+
+
+WORKLOADS = {'spring': _spring, 'burgers': _burgers, 'allen_cahn': _allen_cahn, 'ldc': _ldc, 'cylinder': _cylinder,
+             'cylinder_unsteady': _cylinder_unsteady}
 
 
 def sample_groups(wl: Workload, n_col: int, n_bnd: int, seed: int) -> Dict[str, Tensor]:
@@ -353,3 +371,53 @@ def step(wl: Workload, params: Sequence[Tensor], groups: Dict[str, Tensor]):
     return dict(streams={k: v.detach() for k, v in s_all.items()},
                 row_names=row_names, rows=torch.stack(row_vals).detach(),
                 total=total.detach(), grads=[g.detach() for g in grads])
+
+
+def step_chunked(wl: Workload, params: Sequence[Tensor], groups: Dict[str, Tensor], chunk: int = 8192,
+                 keep_streams: bool = True):
+    """`step` for batches too large for one vmap(jacrev(jacrev)) call: the same arithmetic evaluated chunk by chunk.
+
+    Every loss row is a mean over its group (loss.py:26,57) and every tutorial's recombination is linear in the rows, so
+    total = sum_rows c_row * (1/N_g) * sum_chunks sum_i w_i r_i^2 and d(total)/d(params) accumulates over chunks.  The
+    coefficients c_row are read off `wl.combine` by autograd.  Runs in the dtype / on the device of `params` (the large-batch
+    GPU parity tests run it in float64 on the B200 -- as the checker only)."""
+    params = [p.detach().clone().requires_grad_(True) for p in params]
+    imap = wl.index_map()
+    dev, dtype = params[0].device, params[0].dtype
+    # pass 0: row layout and the combination coefficients (from one point per group)
+    layout = []
+    with torch.no_grad():
+        for gname, xg in groups.items():
+            o = {k: torch.zeros(1, dtype=dtype, device=dev) for k in imap}
+            for loss_type, rname, _, _ in wl.rows(gname, xg[:1].to(dev, dtype), o):
+                layout.append((loss_type, gname, rname))
+    leaves = torch.zeros(len(layout), dtype=dtype, device=dev, requires_grad=True)
+    type_sums = {}
+    for i, (lt, _, _) in enumerate(layout):
+        type_sums[lt] = type_sums.get(lt, 0.0) + leaves[i]
+    coef = torch.autograd.grad(wl.combine(type_sums), leaves)[0]
+    rows = torch.zeros(len(layout), dtype=dtype, device=dev)
+    grads = [torch.zeros_like(p) for p in params]
+    streams_out = {k: [] for k in imap} if keep_streams else None
+    r0 = 0
+    for gname, xg in groups.items():
+        n_g = xg.shape[0]
+        n_rows_g = sum(1 for _, g, _ in layout if g == gname)
+        for lo in range(0, n_g, chunk):
+            xc = xg[lo:lo + chunk].to(dev, dtype)
+            s = streams(params, xc, imap, wl.activation)
+            part = torch.stack([(w * torch.abs(r).pow(2)).sum() / n_g if torch.is_tensor(w) else w * torch.abs(r).pow(2).sum() / n_g
+                                for _, _, r, w in wl.rows(gname, xc, s)])
+            g = torch.autograd.grad((coef[r0:r0 + n_rows_g] * part).sum(), params, allow_unused=True)
+            for acc, gi in zip(grads, g):
+                if gi is not None:
+                    acc += gi
+            rows[r0:r0 + n_rows_g] += part.detach()
+            if keep_streams:
+                for k, v in s.items():
+                    streams_out[k].append(v.detach())
+            del s, part, g
+        r0 += n_rows_g
+    total = (coef * rows).sum()
+    return dict(streams={k: torch.cat(v) for k, v in streams_out.items()} if keep_streams else None,
+                row_names=[f'{lt}/{g}/{r}' for lt, g, r in layout], rows=rows, total=total, grads=grads)

@@ -17,90 +17,16 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-import ref_shim  # noqa: E402
-
-ref_shim.install()
-from torch_DE.continuous import DE_Getter  # noqa: E402
-from torch_DE.continuous.Networks import MLP  # noqa: E402
-from torch_DE.equations import DE_func  # noqa: E402
-from torch_DE.utils import Loss_handler  # noqa: E402
-from torch_DE.utils.data import PINN_dataset  # noqa: E402
 
 from oracle import ref_autograd as O  # noqa: E402
+from oracle import ref_live as RL  # noqa: E402
+
+R = RL.activate()
+DE_Getter, PINN_dataset = R.DE_Getter, R.PINN_dataset
+reference_losses, combine, run_reference = RL.reference_losses, RL.combine, RL.run_reference
 
 torch.set_num_threads(8)
-
-
-def build_net(wl, params, dtype):
-    n = wl.net
-    if wl.name == 'spring':                                   # Tutorials/Spring.py:36
-        net = torch.nn.Sequential(torch.nn.Linear(1, n['width']), torch.nn.Tanh(), torch.nn.Linear(n['width'], 1))
-        lins = [net[0], net[2]]
-    else:
-        net = MLP(n['d_in'], n['n_out'], n['width'], n['n_act'] - 1, activation=wl.activation)
-        lins = list(net.layers) + [net.linear_out]
-    with torch.no_grad():
-        for i, lin in enumerate(lins):
-            lin.weight.copy_(params[2 * i])
-            lin.bias.copy_(params[2 * i + 1])
-    return net.to(dtype), lins
-
-
-def reference_losses(wl, dataset):
-    """Loss table built with the reference's own Loss_handler, mirroring each tutorial."""
-    L = Loss_handler(dataset)
-    pi = torch.pi
-    if wl.name == 'spring':
-        L.add_initial_condition('initial condition', {'u': 0., 'u_t': 1.})
-        L.add_residual('collocation_points', {'spring_eq': DE_func(lambda u, u_tt, **kw: u_tt + u)})
-    elif wl.name == 'burgers':
-        L.add_initial_condition('initial condition', {'u': DE_func(lambda x, **kw: -torch.sin(pi * x))})
-        L.add_boundary('x0', {'u': 0})
-        L.add_boundary('x1', {'u': 0})
-        L.add_residual('collocation points',
-                       {'burgers1D': DE_func(lambda u, u_t, u_x, u_xx, **kw: u_t + u * u_x - (0.01 / pi) * u_xx)})
-    elif wl.name == 'allen_cahn':
-        L.add_initial_condition('t0', {'u': DE_func(lambda x, **kw: x ** 2 * torch.cos(pi * x))})
-        L.add_residual('collocation points',
-                       {'AllenCahn': DE_func(lambda u_t, u_xx, u, **kw: u_t - 0.0001 * u_xx + 5 * u ** 3 - 5 * u)})
-    elif wl.name in ('ldc', 'ldc_small'):
-        sx = DE_func(lambda u, v, u_x, u_y, u_xx, u_yy, p_x, Re=100, **kw: u * u_x + v * u_y + p_x - 1 / Re * (u_xx + u_yy))
-        sy = DE_func(lambda u, v, v_x, v_y, v_xx, v_yy, p_y, Re=100, **kw: u * v_x + v * v_y + p_y - 1 / Re * (v_xx + v_yy))
-        inc = DE_func(lambda u_x, v_y, **kw: u_x + v_y)
-        sdf = DE_func(lambda x, y, **kw: torch.minimum(0.1 - x.abs(), 0.1 - y.abs()))
-        L.add_boundary('no slip', {'u': 0, 'v': 0})
-        L.add_boundary('inlet', {'u': 1, 'v': 0}, weighting={'u': DE_func(lambda x, **kw: 1 - 10 * torch.abs(x)), 'v': 1})
-        L.add_residual('collocation points', {'stokes_x': sx, 'stokes_y': sy, 'incomp': inc}, weighting=sdf)
-    else:
-        raise KeyError(wl.name)
-    return L
-
-
-def combine(wl, type_losses):
-    d = {k: type_losses[k] for k in type_losses.index}
-    return wl.combine(d)
-
-
-def run_reference(wl, params, groups, dtype):
-    net, lins = build_net(wl, params, dtype)
-    dataset = PINN_dataset(wl.input_vars)
-    for gname, xg in groups.items():
-        dataset.add_group(gname, xg.to(dtype), batch_size=xg.shape[0])
-    batch = dataset[{g: torch.arange(x.shape[0]) for g, x in groups.items()}]
-    pinn = DE_Getter(net, wl.input_vars, wl.output_vars, list(wl.derivatives))
-    out = pinn.calculate(batch)
-    loss = reference_losses(wl, dataset)(batch, out)
-    total = combine(wl, loss.grouped_losses('loss_type'))
-    total.backward()
-    df = loss.get_DataFrame()
-    row_names = [f"{r['loss_type']}/{r['group']}/{r['variable']}" for _, r in df.iterrows()]
-    rows = torch.stack(list(df['aggregated_loss'])).detach()
-    grads = []
-    for lin in lins:
-        grads += [lin.weight.grad.detach().clone(), lin.bias.grad.detach().clone()]
-    return ({k: v.detach() for k, v in out['all'].items()}, dict(pinn.derivatives), row_names, rows, total.detach(), grads)
 
 
 CASES = [
@@ -110,12 +36,15 @@ CASES = [
     ('allen_cahn', O.WORKLOADS['allen_cahn'], 64, 16, 13, False),
     ('ldc_small', lambda: O._ldc(width=64, n_act=4, name='ldc_small'), 80, 24, 14, True),
     ('ldc', O.WORKLOADS['ldc'], 48, 12, 15, False),
+    # Tutorials/Stokes_Cylinder.py + Equations/NavierStokes.py:25-80: get_NavierStokes(2, steady_state, Re=100) on MLP 10x512
+    ('cylinder', O.WORKLOADS['cylinder'], 40, 8, 17, False),                      # steady, J = 5
+    ('cylinder_unsteady', O.WORKLOADS['cylinder_unsteady'], 40, 8, 18, False),    # x, y, t: J = 6
 ]
 
 
 def fourier_case():
     """AllenCahn tutorial network: Fourier_Net(2,1,100,4,RWF=True) (Tutorials/AllenCahn.py:65) on the Allen-Cahn loss table."""
-    from torch_DE.continuous.Networks import Fourier_Net
+    Fourier_Net = R.Fourier_Net
     wl = O.WORKLOADS['allen_cahn']()
     groups = O.sample_groups(wl, 64, 16, 16)
     blob = {}
@@ -153,8 +82,80 @@ def fourier_case():
     print('allen_cahn_fourier total32', float(blob['total32']), 'total64', float(blob['total64']), os.path.getsize(path), 'bytes')
 
 
+def fd_engine_case():
+    """The reference's FD_engine (Engines/FD.py:4-133) on MLP(2,2,64,2): central differences with an sdf-clipped step, plain
+    tensor input and a grouped (PINN_dict) input."""
+    blob = {}
+    params = O.init_mlp_params(2, 2, 64, 3, seed=4)
+    x = torch.rand(200, 2, generator=torch.Generator().manual_seed(6)) * 0.8 + 0.1
+    sdf = lambda p_: torch.minimum(p_[:, 0], p_[:, 1])            # noqa: E731
+    ders = ['u_x', 'u_yy', 'v_y']
+    for tag, dtype in (('32', torch.float32), ('64', torch.float64)):
+        net = R.MLP(2, 2, 64, 2).to(dtype)
+        lins = list(net.layers) + [net.linear_out]
+        with torch.no_grad():
+            for i, lin in enumerate(lins):
+                lin.weight.copy_(params[2 * i]); lin.bias.copy_(params[2 * i + 1])
+        pinn = DE_Getter(net, ['x', 'y'], ['u', 'v'], ders)
+        pinn.set_deriv_method('FD', dxs=[1e-2, 2e-2], sdf=sdf)
+        out = pinn.calculate(x.to(dtype))['all']
+        blob['names'] = np.array(list(out.keys()))
+        for k, v in out.items():
+            blob[f's{tag}_{k}'] = v.detach().numpy()
+        out['u_yy'].mean().backward()
+        for i, lin in enumerate(lins):
+            blob[f'g{tag}_{2 * i}'] = lin.weight.grad.numpy().copy()
+            blob[f'g{tag}_{2 * i + 1}'] = lin.bias.grad.numpy().copy()
+        dataset = PINN_dataset(['x', 'y'])
+        dataset.add_group('a', x[:50].to(dtype), batch_size=50)
+        dataset.add_group('b', x[50:].to(dtype), batch_size=150)
+        batch = dataset[{'a': torch.arange(50), 'b': torch.arange(150)}]
+        # (target_groups raises inside the reference: FD.py:61 builds a plain dict that base.py:16-30 rejects)
+        grouped = pinn.calculate(batch)
+        blob['group_a_names'] = np.array(list(grouped['a'].keys()))
+        blob['group_b_names'] = np.array(list(grouped['b'].keys()))
+        for g in ('a', 'b'):
+            for k, v in grouped[g].items():
+                blob[f'grp{tag}_{g}_{k}'] = v.detach().numpy()
+    blob['x'] = x.numpy()
+    for i, p_ in enumerate(params):
+        blob[f'p_{i}'] = p_.numpy()
+    path = os.path.join(HERE, 'fd_engine.npz')
+    np.savez_compressed(path, **blob)
+    print('fd_engine', list(blob['names']), os.path.getsize(path), 'bytes')
+
+
+def gradnorm_case():
+    """The reference's GradNorm (utils/Loss_weighting.py:30-50; call site Tutorials/Stokes_Cylinder.py:107-110) on the
+    ldc_small loss table: k x autograd.grad(retain_graph=True, allow_unused=True) -> norm-balanced weights."""
+    wl = O._ldc(width=64, n_act=4, name='ldc_small')
+    params = O.init_mlp_params(2, 3, 64, 4, seed=1234)
+    groups = O.sample_groups(wl, 80, 24, 14)
+    blob = {}
+    for tag, dtype in (('32', torch.float32), ('64', torch.float64)):
+        live = RL.LiveStep(wl, [p_.to(dtype) for p_ in params], groups, dtype)
+        out = live.pinn.calculate(live.batch)
+        rows = live.handler(live.batch, out).individual_losses()
+        w0 = torch.linspace(0.5, 2.0, len(rows), dtype=dtype)
+        w1 = R.GradNorm(live.net, w0, *rows)
+        w2 = R.GradNorm(live.net, w0, *rows, alpha=0.5, max_weight=50.0)
+        ps = list(live.net.parameters())
+        mags = [torch.sqrt(sum(g.pow(2).sum() for g in torch.autograd.grad(r, ps, retain_graph=True, allow_unused=True) if g is not None))
+                for r in rows]
+        blob['w0'] = w0.double().numpy()
+        blob['w1_' + tag] = w1.detach().double().numpy()
+        blob['w2_' + tag] = w2.detach().double().numpy()
+        blob['mags_' + tag] = torch.stack(mags).detach().double().numpy()
+        blob['rows_' + tag] = rows.detach().double().numpy()
+    path = os.path.join(HERE, 'gradnorm.npz')
+    np.savez_compressed(path, **blob)
+    print('gradnorm', blob['w1_64'], os.path.getsize(path), 'bytes')
+
+
 def main():
     fourier_case()
+    fd_engine_case()
+    gradnorm_case()
     for fixture, factory, n_col, n_bnd, seed, store_params in CASES:
         wl = factory()
         n = wl.net

@@ -7,7 +7,7 @@ import torch
 from oracle import ref_autograd as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FIXTURES = ['spring', 'burgers', 'allen_cahn', 'ldc_small', 'ldc']
+FIXTURES = ['spring', 'burgers', 'allen_cahn', 'ldc_small', 'ldc', 'cylinder', 'cylinder_unsteady']
 
 
 def factory(fixture):

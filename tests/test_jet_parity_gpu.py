@@ -297,9 +297,13 @@ def test_tensor_core_path_shapes(case, n_pts):
 def test_tensor_core_and_ffma_paths_agree(monkeypatch):
     z, owl, params, groups = load('ldc')
     res = {}
+    from torch_de_b200 import _lib
     for no_tc in ('1', '0'):
-        monkeypatch.setenv('TDE_NO_TC', no_tc)
-        res[no_tc] = run_product('ldc')
+        _lib.set_option('no_tc', int(no_tc))
+        try:
+            res[no_tc] = run_product('ldc')
+        finally:
+            _lib.set_option('no_tc', 0)
     for k in res['0'][4].derivatives:
         assert rel_l2(res['0'][5]['all'][k].detach().cpu(), res['1'][5]['all'][k].detach().cpu()) < TOL_STREAM
     g0 = torch.cat([g.flatten() for g in res['0'][8]])
@@ -312,9 +316,13 @@ def test_cta_pair_kernels_match_reference_and_single_cta(monkeypatch):
     reference's float64 run, and agreement with the default single-CTA kernels."""
     z, owl, params, groups = load('ldc')
     res = {}
+    from torch_de_b200 import _lib
     for pair in ('0', '1'):
-        monkeypatch.setenv('TDE_TC_PAIR', pair)
-        res[pair] = run_product('ldc')
+        _lib.set_option('tc_pair', int(pair))
+        try:
+            res[pair] = run_product('ldc')
+        finally:
+            _lib.set_option('tc_pair', 0)
     for k in res['1'][4].derivatives:
         a, b = res['1'][5]['all'][k].detach().cpu(), res['0'][5]['all'][k].detach().cpu()
         assert rel_l2(a, b) < TOL_STREAM
@@ -323,7 +331,11 @@ def test_cta_pair_kernels_match_reference_and_single_cta(monkeypatch):
     g0 = torch.cat([g.flatten() for g in res['0'][8]])
     assert rel_l2(g1, g0) < 1e-5
     # and it is bitwise repeatable (slab copies per thread, fixed-order reduction)
-    again = run_product('ldc')
+    _lib.set_option('tc_pair', 1)
+    try:
+        again = run_product('ldc')
+    finally:
+        _lib.set_option('tc_pair', 0)
     for x, y in zip(res['1'][8], again[8]):
         assert torch.equal(x, y)
 
@@ -422,41 +434,6 @@ def test_rwf_mlp_matches_plain_mlp_with_same_effective_weights():
     for a, b in zip(list(rwf.layers) + [rwf.linear_out], list(plain.layers) + [plain.linear_out]):
         assert rel_l2((a.v.grad * a.s).cpu() , (b.weight.grad * a.s * a.s).cpu()) < 1e-5     # dL/dv = dL/dW * s
         assert rel_l2(a.s.grad.cpu(), (b.weight.grad * a.v).sum(1, keepdim=True).cpu()) < 1e-5
-
-
-def test_fd_engine_matches_reference_formulas():
-    """FD_engine (Engines/FD.py:24-43,109-133) -- 2d+1 value passes in one launch, central differences."""
-    torch.manual_seed(4)
-    net = T.MLP(2, 2, 64, 2).cuda()
-    x = (torch.rand(200, 2, generator=torch.Generator().manual_seed(6)) * 0.8 + 0.1).cuda()
-    pinn = T.DE_Getter(net, ['x', 'y'], ['u', 'v'], ['u_x', 'u_yy', 'v_y'])
-    pinn.set_deriv_method('FD', dxs=[1e-2, 2e-2], sdf=lambda p_: torch.minimum(p_[:, 0], p_[:, 1]))
-    out = pinn(x)['all']
-    with torch.no_grad():                                   # the reference's recipe evaluated with the plain torch net in float64
-        net64 = T.MLP(2, 2, 64, 2).double().cuda()
-        net64.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
-        xd = x.double()
-        sd = torch.minimum(xd[:, 0], xd[:, 1])
-        hx, hy = torch.minimum(sd, torch.tensor(1e-2, device='cuda')), torch.minimum(sd, torch.tensor(2e-2, device='cuda'))
-        def shifted(i, h): y = xd.clone(); y[:, i] += h; return net64(y)
-        u = net64(xd)
-        ref = {'u': u[:, 0], 'v': u[:, 1],
-               'u_x': (shifted(0, hx)[:, 0] - shifted(0, -hx)[:, 0]) / (2 * hx),
-               'u_yy': (shifted(1, -hy)[:, 0] - 2 * u[:, 0] + shifted(1, hy)[:, 0]) / hy.pow(2),
-               'v_y': (shifted(1, hy)[:, 1] - shifted(1, -hy)[:, 1]) / (2 * hy)}
-    assert set(out) == {'u', 'v', 'u_x', 'u_yy', 'u_y', 'v_y'}      # u_yy registers its prefix u_y too (DE_module.py:115-122)
-    for k in ('u', 'v'):
-        assert rel_l2(out[k].detach().cpu(), ref[k].cpu()) < 5e-6
-    assert rel_l2(out['u_x'].detach().cpu(), ref['u_x'].cpu()) < 1e-4          # FP32 value noise / (2h)
-    assert rel_l2(out['v_y'].detach().cpu(), ref['v_y'].cpu()) < 1e-4
-    assert rel_l2(out['u_yy'].detach().cpu(), ref['u_yy'].cpu()) < 5e-2         # FP32 value noise / h^2
-    out['u_yy'].mean().backward()
-    assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in net.parameters())
-    batch = T.make_batch(['x', 'y'], {'a': x[:50], 'b': x[50:]})
-    grouped = pinn.calculate(batch, target_groups='b')
-    assert set(grouped['a']) == {'u', 'v'} and set(grouped['b']) == set(out)
-    with pytest.raises(ValueError):
-        T.FD_engine(net, {'u': (0,), 'u_xy': (0, 0, 1)}, dxs=[1e-3, 1e-3])
 
 
 def test_gradnorm_weights_follow_reference_rule():

@@ -1,0 +1,129 @@
+"""GPU parity AT BENCHMARK SCALE: the same public-API step bench.py times, against the oracle evaluated in float64 on the
+B200 chunk by chunk (`oracle.ref_autograd.step_chunked` -- the checker only; it restates the reference's
+vmap(jacrev(jacrev)) + Loss rows + autograd step, pinned by tests/test_oracle_golden.py).
+
+What these sizes exercise that the golden fixtures (<= 168 points) cannot:
+  * every persistent CTA walks tens of 16-point tiles (steady-state weight pipeline, tile-pair padding at an odd tile count),
+  * the split-K weight-gradient GEMM crosses its accumulator flush several times per CTA (kDwFlushTiles tiles per flush),
+  * gradient slabs accumulate thousands of points per CTA before the fixed-order second-stage reduction,
+  * W = 512 (cylinder 10x512; steady J = 5, unsteady x,y,t J = 6, sin activation), stash mode and multi-chunk recompute mode.
+
+Tolerances are the north star's: <= 1e-5 (relL2 and max|d|/max|ref|) on u and every derivative, <= 1e-4 on every loss row, the
+total and the flat parameter gradient.
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import torch_de_b200 as T
+from torch_de_b200 import _lib
+from torch_de_b200 import workloads as WL
+from oracle import ref_autograd as O
+from tests.golden_util import max_rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_STREAM, TOL_LOSS = 1e-5, 1e-4
+
+
+def _run_case(wl, owl, n_col, n_bnd, seed, oracle_chunk, expect_paths=None, stash_fraction=None, monkeypatch=None):
+    dev = torch.device('cuda')
+    n = owl.net
+    params = O.init_mlp_params(n['d_in'], n['n_out'], n['width'], n['n_act'], seed=1234)
+    groups = O.sample_groups(owl, n_col, n_bnd, seed=seed)
+    net = wl.make_net()
+    lins, _ = T.extract_layers(net)
+    with torch.no_grad():
+        for i, lin in enumerate(lins):
+            lin.weight.copy_(params[2 * i])
+            lin.bias.copy_(params[2 * i + 1])
+    net = net.to(dev)
+    if stash_fraction is not None:
+        from torch_de_b200 import engine as E
+        monkeypatch.setattr(E, 'STASH_FRACTION_OF_FREE', stash_fraction)
+    pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+    runner = pinn.deriv_method._full
+    batch = T.make_batch(wl.input_vars, {g: x.to(dev) for g, x in groups.items()})
+    out = pinn.calculate(batch)
+    handler = wl.build_losses(list(groups.keys()))
+    loss = handler(batch, out)
+    assert set(handler.fusion_report.values()) == {'fused'}, handler.fusion_report
+    total = wl.combine(loss.grouped_losses('loss_type'))
+    total.backward()
+    n_all = sum(x.shape[0] for x in groups.values())
+    if stash_fraction is not None:
+        assert any(runner.chunking.values()), 'the batch was meant to run in recompute mode'
+        chunk = max(runner.chunking.values())
+        assert n_all > 2 * chunk, f'recompute mode should need several chunks (chunk {chunk}, batch {n_all})'
+    got_rows = {f"{r['loss_type']}/{r['group']}/{r['variable']}": float(r['aggregated_loss']) for r in loss.losses}
+    got_grad = torch.cat([p.grad.flatten() for lin in lins for p in (lin.weight, lin.bias)]).double()
+
+    ref = O.step_chunked(owl, [p.double().to(dev) for p in params], {g: x for g, x in groups.items()}, chunk=oracle_chunk)
+    worst = 0.0
+    for name in pinn.derivatives:
+        a, b = out['all'][name].detach(), ref['streams'][name]
+        assert a.shape == b.shape == (n_all,)
+        e2, em = rel_l2(a, b), max_rel(a, b)
+        worst = max(worst, e2, em)
+        assert e2 < TOL_STREAM and em < TOL_STREAM, (name, e2, em)
+    ref_rows = dict(zip(ref['row_names'], [float(v) for v in ref['rows']]))
+    assert set(ref_rows) == set(got_rows)
+    for k, v in got_rows.items():
+        assert abs(v - ref_rows[k]) <= TOL_LOSS * abs(ref_rows[k]) + 1e-12, (k, v, ref_rows[k])
+    assert abs(float(total) - float(ref['total'])) <= TOL_LOSS * abs(float(ref['total']))
+    ref_grad = torch.cat([g.flatten() for g in ref['grads']])
+    eg2, egm = rel_l2(got_grad, ref_grad), max_rel(got_grad, ref_grad)
+    assert eg2 < TOL_LOSS and egm < TOL_LOSS, (eg2, egm)
+    # per-layer: a wrong small tensor (a bias, the input layer) must not hide inside the flat norm
+    o = 0
+    for i, g in enumerate(ref['grads']):
+        k = g.numel()
+        e = rel_l2(got_grad[o:o + k], g)
+        assert e < TOL_LOSS, (i, e)
+        o += k
+    if expect_paths is not None:
+        paths = _lib.lib().tde_plan_paths(C.byref(runner._net), C.byref(runner._spec), n_all)
+        assert paths == expect_paths, f'expected kernel paths {expect_paths}, planned {paths}'
+    print(f'[{owl.name}] {n_all} points: worst stream err {worst:.2e}, grad relL2 {eg2:.2e} max-norm {egm:.2e}')
+
+
+def test_ldc_8x256_past_the_dw_flush_with_odd_tile_count():
+    """LDC 8x256, J = 5 (the benchmark workload): 75 013 collocation points = 4 689 sixteen-point tiles (odd: the last tile pair
+    is padded) -> ~32 tiles per persistent CTA, past the weight-gradient accumulator flush; ragged boundary groups."""
+    _run_case(WL.ldc(), O.WORKLOADS['ldc'](), 75_013, 1_003, seed=31, oracle_chunk=8192, expect_paths=3)
+
+
+def test_allen_cahn_6x128_at_1e5_points():
+    _run_case(WL.allen_cahn(), O.WORKLOADS['allen_cahn'](), 100_003, 1_001, seed=32, oracle_chunk=32768, expect_paths=3)
+
+
+def test_burgers_8x64_at_1e5_points():
+    _run_case(WL.burgers(), O.WORKLOADS['burgers'](), 100_000, 100, seed=33, oracle_chunk=65536, expect_paths=0)
+
+
+@pytest.mark.parametrize('variant', ['steady', 'unsteady', 'steady_sin'])
+def test_cylinder_10x512(variant):
+    """MLP 10x512 (Tutorials/Stokes_Cylinder.py / Unsteady_Cylinder.py scale): steady J = 5, unsteady x,y,t J = 6, sin."""
+    if variant == 'unsteady':
+        wl, owl = WL.cylinder_unsteady(), O.WORKLOADS['cylinder_unsteady']()
+    else:
+        act = 'sin' if variant.endswith('sin') else 'tanh'
+        wl, owl = WL.cylinder(activation=act), O._cylinder(activation=act)
+    _run_case(wl, owl, 40_005, 403, seed=34, oracle_chunk=2048, expect_paths=3)
+
+
+def test_cylinder_10x512_multi_chunk_recompute(monkeypatch):
+    """Same workload with the stash budget forced tiny: the backward re-runs the forward chunk by chunk (several chunks)."""
+    free, _ = torch.cuda.mem_get_info()
+    # stash ~ L*W*J*4 B = 102 KB per point: allow about 10 000 points' worth
+    frac = 1.0e9 / free
+    _run_case(WL.cylinder(), O.WORKLOADS['cylinder'](), 40_005, 403, seed=35, oracle_chunk=2048, expect_paths=3,
+              stash_fraction=frac, monkeypatch=monkeypatch)
+
+
+def test_ldc_8x256_multi_chunk_recompute(monkeypatch):
+    free, _ = torch.cuda.mem_get_info()
+    frac = 1.5e9 / free
+    _run_case(WL.ldc(), O.WORKLOADS['ldc'](), 75_013, 1_003, seed=36, oracle_chunk=8192, expect_paths=3,
+              stash_fraction=frac, monkeypatch=monkeypatch)

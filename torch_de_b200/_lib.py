@@ -34,7 +34,7 @@ class TdePlan(C.Structure):
     _fields_ = [("n_channels", C.c_int32), ("width_padded", C.c_int32), ("tile_points", C.c_int32),
                 ("n_ctas", C.c_int32), ("n_tiles", C.c_int64), ("stash_bytes", C.c_int64),
                 ("workspace_bytes", C.c_int64), ("n_params", C.c_int64), ("smem_forward", C.c_int32),
-                ("smem_backward", C.c_int32)]
+                ("smem_backward", C.c_int32), ("workspace_forward_bytes", C.c_int64)]
 
 
 class TdeOp(C.Structure):
@@ -49,7 +49,7 @@ class TdeLossProgram(C.Structure):
 
 EXPORTS = ["tde_last_error", "tde_version", "tde_abi_struct_bytes", "tde_plan", "tde_jet_forward", "tde_jet_backward",
            "tde_residual_loss", "tde_adam_step", "tde_fp32_peak_probe", "tde_launch_count", "tde_profile_begin",
-           "tde_profile_end", "tde_profile_kind", "tde_plan_paths", "tde_grid_interp2d"]
+           "tde_profile_end", "tde_profile_kind", "tde_plan_paths", "tde_grid_interp2d", "tde_set_option"]
 
 _LIB = None
 
@@ -72,6 +72,7 @@ def _declare(lib):
     lib.tde_profile_kind.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
     lib.tde_plan_paths.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), i64]
     lib.tde_grid_interp2d.argtypes = [vp, i32, vp, i32, vp, vp, vp, i64, vp, vp]
+    lib.tde_set_option.argtypes = [C.c_char_p, C.c_int]
     lib.tde_launch_count.restype = C.c_longlong
     lib.tde_launch_count.argtypes = []
     return lib
@@ -93,6 +94,23 @@ def lib():
                                    f"{handle.tde_abi_struct_bytes(i)} vs {C.sizeof(st)} bytes): rebuild it")
         _LIB = handle
     return _LIB
+
+
+def set_option(name: str, value: int) -> None:
+    """Override a run-time switch of the library (see tde_set_option in include/tde_jet.h)."""
+    check(lib().tde_set_option(name.encode(), int(value)), "tde_set_option")
+
+
+def on_device(device):
+    """Context manager: make `device` the process's current CUDA device around a library call.  The kernels, the
+    cudaFuncSetAttribute / occupancy queries and the SM-count lookup inside libtde_jet.so all act on the current device,
+    which is not necessarily the device the tensors live on (several GPUs in one process, DP ranks that only use
+    `.to(f'cuda:{rank}')`)."""
+    import contextlib
+    import torch
+    if getattr(device, 'type', None) == 'cuda':
+        return torch.cuda.device(device)
+    return contextlib.nullcontext()
 
 
 def check(rc, what):

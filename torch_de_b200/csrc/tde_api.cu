@@ -35,6 +35,27 @@ int fail(const char* fmt, ...) {
 
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in per CTA on sm_100
 
+// ---- run-time switches (A/B measurements, debugging).  The environment is read ONCE, at the first call into the library;
+// tde_set_option() overrides a switch afterwards.  Nothing on the per-launch path calls getenv.
+struct Options {
+    int no_tc = 0;        // TDE_NO_TC=1: FFMA2 kernels for every width
+    int no_tc_bwd = 0;    // TDE_NO_TC_BWD=1: tensor-core forward, FFMA2 reverse sweep
+    int tc_pair = 0;      // TDE_TC_PAIR=1: cta_group::2 kernels for W = 256
+    int tc_slots = 0;     // TDE_TC_SLOTS=n: cap on resident clusters of the tensor-core kernels (0 = no cap)
+    int tc_stages = 0;    // TDE_TC_STAGES=n: cap on weight stages (0 = as many as fit)
+    int tc_dbg = 0;       // TDE_TC_DBG bit 2: tile-level cycle stamps (synchronises!)
+};
+Options& options() {
+    static Options o = [] {
+        Options v;
+        auto rd = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
+        v.no_tc = rd("TDE_NO_TC"); v.no_tc_bwd = rd("TDE_NO_TC_BWD"); v.tc_pair = rd("TDE_TC_PAIR");
+        v.tc_slots = rd("TDE_TC_SLOTS"); v.tc_stages = rd("TDE_TC_STAGES"); v.tc_dbg = rd("TDE_TC_DBG");
+        return v;
+    }();
+    return o;
+}
+
 // ---- instrumentation: launch counter and per-kernel CUDA-event timing (bench.py roofline) ----
 long long g_launches = 0;
 bool g_profiling = false;
@@ -79,12 +100,13 @@ const Dispatch kDispatch[] = {TDE_SPEC_LIST(TDE_ROW)};
 
 // resident-cluster capacity of the pair kernels, cached per (spec, smem)
 int sm_count();
+int current_device();
 
 int pair_cluster_capacity(const Dispatch* d, int smem) {
     static std::mutex mu;
-    static std::map<std::pair<const Dispatch*, int>, int> cache;
+    static std::map<std::pair<const Dispatch*, std::pair<int, int>>, int> cache;
     std::lock_guard<std::mutex> lock(mu);
-    auto key = std::make_pair(d, smem);
+    auto key = std::make_pair(d, std::make_pair(smem, current_device()));
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     const int n = d->pair_max_clusters(smem);
@@ -102,7 +124,7 @@ int tc_cluster_slots(const Dispatch* d, bool pair, int smem) {
         if (cap > 0) slots = std::min(slots, cap);
         else (void)cudaGetLastError();
     }
-    if (const char* e = getenv("TDE_TC_SLOTS")) slots = std::min(slots, std::max(1, atoi(e)));   // experiments only
+    if (options().tc_slots > 0) slots = std::min(slots, options().tc_slots);   // experiments only
     return std::max(1, slots);
 }
 
@@ -140,18 +162,26 @@ struct Geometry {
     const Dispatch* disp;
 };
 
+// SM count of the CURRENT device (the Python binding makes the tensors' device current around every call), cached per device
 int sm_count() {
-    static int cached = 0;
-    if (cached) return cached;
+    static int cached[64] = {0};
     int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
-        cached = n;
-    } else {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
         (void)cudaGetLastError();
-        cached = 148;  // planning without a device (unit tests on CPU): B200 has 148 SMs
+        return 148;  // planning without a device (unit tests on CPU): B200 has 148 SMs
     }
-    return cached;
+    if (cached[dev]) return cached[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+        cached[dev] = n;
+        return n;
+    }
+    (void)cudaGetLastError();
+    return 148;
+}
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    return dev;
 }
 
 int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry* G) {
@@ -267,13 +297,12 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     {
         const int Ntc = tde::kTcPoints * g.J;
         const int mb = g.W / 128;
-        const char* no_tc = getenv("TDE_NO_TC");
+        const bool no_tc = options().no_tc != 0;
         // W = 128: single-CTA kernels, N = 16 J columns per MMA.  W = 256: CTA-pair kernels (cta_group::2), N = 32 J <= 256.
         // TDE_TC_PAIR=1 (W = 256, N = 32 J <= 256): CTA-pair kernels (cta_group::2) instead of the single-CTA ones
-        const char* pair_env = getenv("TDE_TC_PAIR");
-        g.use_pair = g.W == 256 && 6 * Ntc <= 512 && pair_env && pair_env[0] == '1';
+        g.use_pair = g.W == 256 && 6 * Ntc <= 512 && options().tc_pair == 1;
         const bool shape_ok = (g.W == 128 || g.W == 256) && (g.use_pair || tde::tc_shape_ok(mb, Ntc));
-        if (shape_ok && L >= 2 && g.TP % tde::kTcPoints == 0 && !(no_tc && no_tc[0] == '1')) {
+        if (shape_ok && L >= 2 && g.TP % tde::kTcPoints == 0 && !no_tc) {
             const int64_t atomk = (Ntc / 8) * 1024;
             const int pts = g.use_pair ? 2 * tde::kTcPoints : tde::kTcPoints;     // points staged per CTA (x, seeds)
             // [planes][weight stages][w_out][x][seeds | y, 4 (padded) outputs per channel][tail: barriers]; the pair kernels keep a 1 KB header
@@ -282,7 +311,7 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
             const int64_t chunk = g.use_pair ? tde::kPairChunkBytes : (int64_t)mb * 2 * 2 * 2048;
             for (int st = tde::kTcMaxStages; st >= 2; --st)
                 if (fixed + st * chunk <= kSmemLimit) {
-                    if (const char* fs = getenv("TDE_TC_STAGES")) st = std::max(2, std::min(st, atoi(fs)));   // experiments only
+                    if (options().tc_stages > 0) st = std::max(2, std::min(st, options().tc_stages));   // experiments only
                     g.use_tc = 1; g.tc_mb = mb; g.tc_stages = st; g.tc_smem = (int)(fixed + st * chunk);
                     g.tc_nacc = tde::tc_acc_sets(g.use_pair ? 1 : mb, g.use_pair ? 2 * Ntc : Ntc);
                     break;
@@ -294,9 +323,8 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     g.o_wc = o;   if (g.use_tc) o += (int64_t)(L - 1) * 2 * WW;
     g.use_tc_bwd = 0;
     {
-        const char* no_b = getenv("TDE_NO_TC_BWD");
         g.dw_smem = 1024 + (tde::kDwStages * 4 + tde::dw_raw_stages(g.J) * 2) * g.W * 32;
-        if (g.use_tc && g.J <= 6 && g.dw_smem <= kSmemLimit && !(no_b && no_b[0] == '1')) {
+        if (g.use_tc && g.J <= 6 && g.dw_smem <= kSmemLimit && !options().no_tc_bwd) {
             g.use_tc_bwd = 1;
             g.rsplit = 1;      // the FFMA dW phase (and its column split) is not used on this path
         }
@@ -574,14 +602,18 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
 constexpr int kLossBlocks = 592;  // 148 SMs x 4
 constexpr int kLossThreads = 256;
 
-__device__ float g_loss_partials[kLossBlocks * TDE_MAX_ROWS];
-__device__ unsigned int g_loss_ticket = 0;
+// cross-block scratch of residual_loss_kernel: a ring of slots handed out round-robin per launch, so launches that are in
+// flight at the same time on different streams never share partials or a ticket
+constexpr int kLossSlots = 32;
+__device__ float g_loss_partials[kLossSlots][kLossBlocks * TDE_MAX_ROWS];
+__device__ unsigned int g_loss_ticket[kLossSlots];
+unsigned long long g_loss_seq = 0;
 
 __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
     const __grid_constant__ TdeLossProgram prog, const float* __restrict__ streams, int64_t ld, int n_stream_rows,
     const float* __restrict__ aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
     const float* __restrict__ coef_dev, float* __restrict__ row_sums, float* __restrict__ seeds,
-    float* __restrict__ point_res) {
+    float* __restrict__ point_res, const int slot) {
     __shared__ float red[TDE_MAX_ROWS][kLossThreads / 32];
     __shared__ bool is_last;
     float part[TDE_MAX_ROWS], coef[TDE_MAX_ROWS];
@@ -645,6 +677,7 @@ __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
                     case TDE_OP_NEG: adj[op.a] -= d; break;
                     case TDE_OP_POWI: {
                         const int e = (int)op.imm;
+                        if (e == 0) break;               // d(b^0) = 0 (b^(e-1) would be 1/b: 0 * inf at b = 0)
                         const float b = v[op.a];
                         float pw = 1.0f;  // b^(e-1)
                         for (int t = 0; t < (e - 1 < 0 ? 1 - e : e - 1); ++t) pw *= b;
@@ -677,20 +710,20 @@ __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
     if (threadIdx.x < TDE_MAX_ROWS) {
         float s = 0.0f;
         for (int w = 0; w < kLossThreads / 32; ++w) s += red[threadIdx.x][w];
-        g_loss_partials[blockIdx.x * TDE_MAX_ROWS + threadIdx.x] = s;
+        g_loss_partials[slot][blockIdx.x * TDE_MAX_ROWS + threadIdx.x] = s;
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&g_loss_ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) is_last = (atomicAdd(&g_loss_ticket[slot], 1u) == gridDim.x - 1);
     __syncthreads();
     if (is_last) {
         __threadfence();
         if (threadIdx.x < prog.n_rows && row_sums) {
             float s = 0.0f;
-            for (unsigned b = 0; b < gridDim.x; ++b) s += g_loss_partials[b * TDE_MAX_ROWS + threadIdx.x];
+            for (unsigned b = 0; b < gridDim.x; ++b) s += g_loss_partials[slot][b * TDE_MAX_ROWS + threadIdx.x];
             row_sums[threadIdx.x] += s * inv_count;
         }
-        if (threadIdx.x == 0) g_loss_ticket = 0;
+        if (threadIdx.x == 0) g_loss_ticket[slot] = 0;
     }
 }
 
@@ -802,6 +835,7 @@ int tde_plan(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points, TdePla
     plan->n_tiles = g.n_tiles;
     plan->stash_bytes = g.stash_total_floats * 4;
     plan->workspace_bytes = g.workspace_floats * 4;
+    plan->workspace_forward_bytes = g.packed_floats * 4;
     plan->n_params = g.n_params;
     plan->smem_forward = g.smem_fwd;
     plan->smem_backward = g.smem_bwd;
@@ -828,7 +862,7 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
         tde::TcParams t{};
         t.x = x; t.B = n_points; t.n_tiles = g.tc_tiles;
         t.d_in = g.d_in; t.n_out = g.n_out; t.L = g.L; t.W = g.W; t.act = g.act; t.MB = g.tc_mb; t.n_stages = g.tc_stages; t.n_acc = g.tc_nacc; t.fourier_half = g.fourier_half; t.pair = g.use_pair;
-        { const char* d = getenv("TDE_TC_DBG"); t.dbg = d ? atoi(d) : 0; }
+        t.dbg = options().tc_dbg;
         static long long* dbg_buf = nullptr;
         if (t.dbg & 4) {
             if (!dbg_buf) { cudaMalloc(&dbg_buf, 64 * sizeof(long long)); cudaMemset(dbg_buf, 0, 64 * sizeof(long long)); }
@@ -905,8 +939,7 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         d.stash_layer_stride = t.stash_layer_stride; d.tiles_per_bw_tile = t.tiles_per_bw_tile;
         d.gpart = t.gpart; d.gp_stride = g.gp_stride; d.gp_off_hidden = g.g_hidden;
         static long long* bdbg = nullptr;
-        const char* dbg_env = getenv("TDE_TC_DBG");
-        if (dbg_env && (atoi(dbg_env) & 4)) {
+        if (options().tc_dbg & 4) {
             if (!bdbg) { cudaMalloc(&bdbg, 64 * sizeof(long long)); cudaMemset(bdbg, 0, 64 * sizeof(long long)); }
             t.dbg_buf = bdbg;
         }
@@ -977,7 +1010,8 @@ int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t 
     if (n == 0) return 0;
     const int blocks = (int)std::min<int64_t>((n + kLossThreads - 1) / kLossThreads, kLossBlocks);
     residual_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(*prog, streams, ld, n_stream_rows, aux, ld_aux,
-                                                                             p0, n, inv_count, coef_dev, row_sums, seeds, point_res);
+                                                                             p0, n, inv_count, coef_dev, row_sums, seeds, point_res,
+                                                                             (int)(g_loss_seq++ % kLossSlots));
     ++g_launches;
     TDE_CUDA(cudaGetLastError());
     return 0;
@@ -999,6 +1033,20 @@ int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
 }
 
 long long tde_launch_count(void) { return g_launches; }
+
+int tde_set_option(const char* name, int value) {
+    if (!name) return fail("null option name");
+    Options& o = options();
+    const std::string n(name);
+    if (n == "no_tc") o.no_tc = value;
+    else if (n == "no_tc_bwd") o.no_tc_bwd = value;
+    else if (n == "tc_pair") o.tc_pair = value;
+    else if (n == "tc_slots") o.tc_slots = value;
+    else if (n == "tc_stages") o.tc_stages = value;
+    else if (n == "tc_dbg") o.tc_dbg = value;
+    else return fail("unknown option '%s' (no_tc, no_tc_bwd, tc_pair, tc_slots, tc_stages, tc_dbg)", name);
+    return 0;
+}
 
 int tde_profile_begin(void) {
     for (auto& t : g_timed) {

@@ -10,6 +10,7 @@ Returned tensors are FP32 `[B_g]` views of one `[J*n_out, B]` block, differentia
 network parameters through `_JetFunction` (forward = tde_jet_forward, backward = tde_jet_backward).
 """
 import ctypes as C
+import sys
 from typing import Dict, List, Optional, Sequence, Union
 
 import torch
@@ -18,19 +19,32 @@ from . import _lib
 from .networks import extract_layers
 from .spec import JetChannels
 
-try:  # when the reference package is importable, be a real subclass so its isinstance check passes
-    from torch_DE.continuous.Engines import engine as _EngineBase  # type: ignore
-except Exception:  # pragma: no cover - the reference is absent on the GPU box
-    class _EngineBase:  # same public surface as Engines/base.py:5-11
-        def __init__(self) -> None:
-            self.derivatives = None
-            self.net = None
-            self.output_vars = None
+class _EngineBase:  # same public surface as the reference's engine base (Engines/base.py:5-11)
+    def __init__(self) -> None:
+        self.derivatives = None
+        self.net = None
+        self.output_vars = None
 
-        def __call__(self, *args, **kwargs):
-            return self.calculate(*args, **kwargs)
+    def __call__(self, *args, **kwargs):
+        return self.calculate(*args, **kwargs)
 
-# tests flip this to exercise host logic against the C oracle on CPU; the product never does
+    def __new__(cls, *args, **kwargs):
+        """The reference installs a custom engine only if `isinstance(obj, torch_DE...engine)` (DE_module.py:148-149).  When
+        the reference package is loaded in this process, instances are created from a subclass that also derives from its
+        `engine`, whatever the import order was."""
+        mod = sys.modules.get('torch_DE.continuous.Engines')
+        ref = getattr(mod, 'engine', None) if mod is not None else None
+        if isinstance(ref, type) and not issubclass(cls, ref):
+            key = (cls, ref)
+            if key not in _MIXED:
+                _MIXED[key] = type(cls.__name__, (cls, ref), {'__module__': cls.__module__})
+            cls = _MIXED[key]
+        return object.__new__(cls)
+
+
+_MIXED: Dict[tuple, type] = {}
+
+# CPU tests flip this to exercise the host-side checks without a device; the product never does (no CPU path exists)
 _REQUIRE_CUDA = True
 
 
@@ -74,7 +88,8 @@ class JetRunner:
             with torch.no_grad():
                 self._bind(self.effective_tensors())
             p = _lib.TdePlan()
-            _lib.check(_lib.lib().tde_plan(C.byref(self._net), C.byref(self._spec), n_points, C.byref(p)), "tde_plan")
+            with _lib.on_device(self.lins[0].module.parameters().__next__().device):
+                _lib.check(_lib.lib().tde_plan(C.byref(self._net), C.byref(self._spec), n_points, C.byref(p)), "tde_plan")
             self._plans[n_points] = p
         return p
 
@@ -125,9 +140,12 @@ class JetRunner:
             stash = self._chunk_stash
         elif need_stash:
             stash = torch.empty(plan.stash_bytes // 4, dtype=torch.float32, device=x.device)
-        ws = self._ws(plan.workspace_bytes, x.device)
-        rc = _lib.lib().tde_jet_forward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, out.data_ptr(), B,
-                                        stash.data_ptr() if need_stash else None, ws.data_ptr(), self._stream(x.device))
+        # a forward that keeps no stash (inference, value-only groups, the first pass of recompute mode) only needs the
+        # packed weights; the full workspace (gradient slabs, Hbar stream) belongs to a forward/backward pair
+        ws = self._ws(plan.workspace_bytes if need_stash else plan.workspace_forward_bytes, x.device)
+        with _lib.on_device(x.device):
+            rc = _lib.lib().tde_jet_forward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, out.data_ptr(), B,
+                                            stash.data_ptr() if need_stash else None, ws.data_ptr(), self._stream(x.device))
         _lib.check(rc, "tde_jet_forward")
         return x, out, stash
 
@@ -148,9 +166,10 @@ class JetRunner:
         plan = self.plan(B)
         self._bind(tensors)
         ws = self._ws(plan.workspace_bytes, x.device)
-        rc = _lib.lib().tde_jet_backward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, stash.data_ptr(),
-                                         seeds.data_ptr(), seeds_ld, grad_scale, flat_grad.data_ptr(), ws.data_ptr(),
-                                         self._stream(x.device))
+        with _lib.on_device(x.device):
+            rc = _lib.lib().tde_jet_backward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, stash.data_ptr(),
+                                             seeds.data_ptr(), seeds_ld, grad_scale, flat_grad.data_ptr(), ws.data_ptr(),
+                                             self._stream(x.device))
         _lib.check(rc, "tde_jet_backward")
         return flat_grad
 
@@ -183,13 +202,17 @@ class _JetFunction(torch.autograd.Function):
                 free, _ = torch.cuda.mem_get_info(x.device)
                 free += torch.cuda.memory_reserved(x.device) - torch.cuda.memory_allocated(x.device)
                 budget = STASH_FRACTION_OF_FREE * free
-                # stash + workspace (the tensor-core backward keeps two more streams of the stash's size in the workspace)
-                total = runner.plan(x.shape[0]).stash_bytes + runner.plan(x.shape[0]).workspace_bytes
+                # stash + workspace (the tensor-core backward keeps an Hbar stream of the stash's size in the workspace)
+                need_bytes = lambda n: runner.plan(n).stash_bytes + runner.plan(n).workspace_bytes      # noqa: E731
                 chunk = 0
-                if total > budget:
-                    n_chunks = int(-(-total // budget))
+                if need_bytes(x.shape[0]) > budget:
                     tile = runner.plan(x.shape[0]).tile_points
-                    chunk = max(tile, -(-(-(-x.shape[0] // n_chunks)) // tile) * tile)
+                    n_chunks = int(-(-need_bytes(x.shape[0]) // budget))
+                    while True:      # fixed costs (weights, gradient slabs) do not shrink with the chunk: re-check the chunk's own plan
+                        chunk = max(tile, -(-(-(-x.shape[0] // n_chunks)) // tile) * tile)
+                        if chunk == tile or need_bytes(chunk) <= budget:
+                            break
+                        n_chunks += 1
                 runner.chunking[key] = chunk
             ctx.chunk = runner.chunking[key]
         xc, out, stash = runner.forward(x, params, need_stash=need and ctx.chunk == 0)

@@ -10,7 +10,7 @@ from typing import Callable, Dict, List
 
 import torch
 
-from .equations import DE_func
+from .equations import DE_func, get_NavierStokes
 from .loss import Loss_handler
 from .networks import MLP
 
@@ -141,12 +141,36 @@ def ldc(width=256, n_act=8, name='ldc'):
                     lambda s: s['residual'] + 100 * s['boundary'], default_points=4_000_000, default_boundary=40_000)
 
 
-def cylinder():
-    lo, hi = [0.0, 0.0], [22.0, 4.1]
-    return Workload('cylinder', ['x', 'y'], ['u', 'v', 'p'], list(_NS_DERIVS), 512, 10,
-                    {'collocation points': _uniform(lo, hi), 'inlet': _edge(0, 0.0, lo, hi), 'no slip': _edge(1, 0.0, lo, hi)},
-                    lambda names: _ns_losses(names, None, None, ('NavierStokes_x', 'NavierStokes_y', 'incompressible')),
-                    lambda s: s['residual'] + 100 * s['boundary'], default_points=16_000_000, default_boundary=40_000)
+_NS_DERIVS_T = ['u_x', 'u_y', 'u_t', 'u_xx', 'u_yy', 'p_x', 'v_x', 'v_y', 'v_t', 'v_xx', 'v_yy', 'p_y']
 
 
-WORKLOADS = {'spring': spring, 'burgers': burgers, 'allen_cahn': allen_cahn, 'ldc': ldc, 'cylinder': cylinder}
+def cylinder(width=512, n_act=10, name='cylinder', steady=True, activation='tanh'):
+    """Cylinder-flow box with the residuals of get_NavierStokes(2, steady_state, Re=100) (Equations/NavierStokes.py:25-80,
+    Tutorials/Stokes_Cylinder.py:65-79); the unsteady variant (Unsteady_Cylinder.py:146) adds t in [0, 1] and an
+    initial-condition group with the parabolic inlet profile of Stokes_Cylinder.py:64."""
+    lo, hi = [0.0, 0.0] + ([] if steady else [0.0]), [22.0, 4.1] + ([] if steady else [1.0])
+
+    def losses(names):
+        _, _, _, eqs = get_NavierStokes(2, steady_state=steady, Re=100)
+        L = Loss_handler(names)
+        L.add_boundary('no slip', {'u': 0, 'v': 0})
+        L.add_boundary('inlet', {'u': 1, 'v': 0})
+        if not steady:
+            L.add_initial_condition('initial condition', {'u': DE_func(lambda y, **kw: 4 * y * (4.1 - y) / 4.1 ** 2), 'v': 0})
+        L.add_residual('collocation points', eqs)
+        return L
+    groups = {'collocation points': _uniform(lo, hi), 'inlet': _edge(0, 0.0, lo, hi), 'no slip': _edge(1, 0.0, lo, hi)}
+    if not steady:
+        groups['initial condition'] = _edge(2, 0.0, lo, hi)
+    return Workload(name, ['x', 'y'] + ([] if steady else ['t']), ['u', 'v', 'p'], list(_NS_DERIVS if steady else _NS_DERIVS_T),
+                    width, n_act, groups, losses,
+                    lambda s: s['residual'] + 100 * s['boundary'] + (0 if steady else 100 * s['initial condition']),
+                    activation=activation, default_points=16_000_000, default_boundary=40_000)
+
+
+def cylinder_unsteady(width=512, n_act=10, name='cylinder_unsteady', activation='tanh'):
+    return cylinder(width, n_act, name, steady=False, activation=activation)
+
+
+WORKLOADS = {'spring': spring, 'burgers': burgers, 'allen_cahn': allen_cahn, 'ldc': ldc, 'cylinder': cylinder,
+             'cylinder_unsteady': cylinder_unsteady}
