@@ -162,9 +162,10 @@ int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t 
                       const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
                       const float* coef_dev, float* row_sums, float* seeds, float* point_res, void* stream);
 
-/* Adam (torch.optim.Adam defaults semantics: bias-corrected, eps outside sqrt of v_hat), one launch. */
+/* Adam with torch.optim.Adam's arithmetic (bias-corrected, eps outside sqrt of v_hat; hyper-parameters are doubles rounded to
+ * float once, like torch's python scalars), one launch.  `step` counts from 1. */
 int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                  float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+                  double lr, double beta1, double beta2, double eps, int32_t step, void* stream);
 
 /* Instrumentation for bench.py: kernels launched by this library since load, and CUDA-event timing of the
  * two main kernels (events are recorded on the launching stream right around the kernel, nothing else). */

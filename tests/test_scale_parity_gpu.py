@@ -27,7 +27,7 @@ pytestmark = pytest.mark.gpu
 TOL_STREAM, TOL_LOSS = 1e-5, 1e-4
 
 
-def _run_case(wl, owl, n_col, n_bnd, seed, oracle_chunk, expect_paths=None, stash_fraction=None, monkeypatch=None):
+def _run_case(wl, owl, n_col, n_bnd, seed, oracle_chunk, expect_paths=None, stash_fraction=None, monkeypatch=None, ref32_floor=False):
     dev = torch.device('cuda')
     n = owl.net
     params = O.init_mlp_params(n['d_in'], n['n_out'], n['width'], n['n_act'], seed=1234)
@@ -60,13 +60,24 @@ def _run_case(wl, owl, n_col, n_bnd, seed, oracle_chunk, expect_paths=None, stas
     got_grad = torch.cat([p.grad.flatten() for lin in lins for p in (lin.weight, lin.bias)]).double()
 
     ref = O.step_chunked(owl, [p.double().to(dev) for p in params], {g: x for g, x in groups.items()}, chunk=oracle_chunk)
+    floor = {}
+    if ref32_floor:
+        # 10x512 on the cylinder box sits on the FP32 noise floor: the reference's own float32 run (same torch.func calls, on
+        # this GPU) is 8e-6 from its float64 run in max-norm at 2 000 points and more over a larger sample.  relL2 keeps the
+        # 1e-5 bar; the max-norm bar is 1e-5 or 1.5x the reference's own float32 distance to the truth, whichever is larger.
+        r32 = O.step_chunked(owl, [p.to(dev) for p in params], {g: x for g, x in groups.items()}, chunk=oracle_chunk)
+        floor = {k: max_rel(r32['streams'][k], ref['streams'][k]) for k in ref['streams']}
+        del r32
     worst = 0.0
     for name in pinn.derivatives:
         a, b = out['all'][name].detach(), ref['streams'][name]
         assert a.shape == b.shape == (n_all,)
         e2, em = rel_l2(a, b), max_rel(a, b)
         worst = max(worst, e2, em)
-        assert e2 < TOL_STREAM and em < TOL_STREAM, (name, e2, em)
+        assert e2 < TOL_STREAM, (name, e2)
+        assert em < max(TOL_STREAM, 1.5 * floor.get(name, 0.0)), (name, em, floor.get(name))
+    if floor:
+        print(f'[{owl.name}] reference float32 max-norm distance to float64, worst stream: {max(floor.values()):.2e}')
     ref_rows = dict(zip(ref['row_names'], [float(v) for v in ref['rows']]))
     assert set(ref_rows) == set(got_rows)
     for k, v in got_rows.items():
@@ -110,7 +121,7 @@ def test_cylinder_10x512(variant):
     else:
         act = 'sin' if variant.endswith('sin') else 'tanh'
         wl, owl = WL.cylinder(activation=act), O._cylinder(activation=act)
-    _run_case(wl, owl, 40_005, 403, seed=34, oracle_chunk=2048, expect_paths=3)
+    _run_case(wl, owl, 40_005, 403, seed=34, oracle_chunk=2048, expect_paths=3, ref32_floor=True)
 
 
 def test_cylinder_10x512_multi_chunk_recompute(monkeypatch):
@@ -119,7 +130,7 @@ def test_cylinder_10x512_multi_chunk_recompute(monkeypatch):
     # stash ~ L*W*J*4 B = 102 KB per point: allow about 10 000 points' worth
     frac = 1.0e9 / free
     _run_case(WL.cylinder(), O.WORKLOADS['cylinder'](), 40_005, 403, seed=35, oracle_chunk=2048, expect_paths=3,
-              stash_fraction=frac, monkeypatch=monkeypatch)
+              stash_fraction=frac, monkeypatch=monkeypatch, ref32_floor=True)
 
 
 def test_ldc_8x256_multi_chunk_recompute(monkeypatch):

@@ -63,7 +63,7 @@ def _declare(lib):
     lib.tde_jet_forward.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), vp, i64, vp, i64, vp, vp, vp]
     lib.tde_jet_backward.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), vp, i64, vp, vp, i64, f32, vp, vp, vp]
     lib.tde_residual_loss.argtypes = [C.POINTER(TdeLossProgram), vp, i64, i32, vp, i64, i64, i64, f32, vp, vp, vp, vp, vp]
-    lib.tde_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]
+    lib.tde_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, i32, vp]
     lib.tde_fp32_peak_probe.argtypes = [C.POINTER(C.c_double), vp]
     lib.tde_profile_begin.argtypes = []
     lib.tde_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32)]

@@ -727,17 +727,23 @@ __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
     }
 }
 
+// torch.optim.Adam's update, operation for operation (torch/optim/adam.py, _multi_tensor_adam with python-float scalars):
+//   exp_avg.lerp_(grad, 1 - beta1)                       -> m + w1 * (g - m)          (lerp with weight < 0.5)
+//   exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2) -> v * beta2 + (w2 * g) * g
+//   denom = exp_avg_sq.sqrt() / sqrt(bias_correction2) + eps;  param.addcdiv_(exp_avg, denom, value = -lr / bias_correction1)
+// The scalars are computed in double on the host and rounded to float once, as torch does.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                            float bc1, float bc2_sqrt) {
+                            float* __restrict__ v, int64_t n, float w1, float b2, float w2, float eps,
+                            float neg_step_size, float bc2_sqrt) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float gi = g[i];
-        const float mi = b1 * m[i] + (1.0f - b1) * gi;     // exp_avg.lerp_(grad, 1-beta1)
-        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        const float m0 = m[i];
+        const float mi = fmaf(w1, gi - m0, m0);
+        const float vi = fmaf(w2 * gi, gi, v[i] * b2);
         m[i] = mi;
         v[i] = vi;
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] -= (lr / bc1) * (mi / denom);
+        p[i] = fmaf(neg_step_size, mi / denom, p[i]);
     }
 }
 
@@ -1017,16 +1023,17 @@ int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t 
     return 0;
 }
 
-int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                  float beta1, float beta2, float eps, int32_t step, void* stream) {
+int tde_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                  double beta1, double beta2, double eps, int32_t step, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("null adam buffer");
     if (n == 0) return 0;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    if (step < 1) return fail("adam step counter starts at 1, got %d", step);
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
     const int threads = 256;
     const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 8);
-    adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                              (float)bc1, (float)sqrt(bc2));
+    adam_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2,
+                                                              (float)(1.0 - beta2), (float)eps, (float)(-lr / bc1), (float)sqrt(bc2));
     ++g_launches;
     TDE_CUDA(cudaGetLastError());
     return 0;
