@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--boundary-per-gpu", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=4096, help="collocation points per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graphed", action="store_true",
+                    help="also time the step replayed as one CUDA graph (torch_de_b200.GraphedStep); reported next to the eager value")
     return ap.parse_args()
 
 
@@ -176,6 +178,29 @@ def gpu_reference_best(workload, dev, sizes=(4096, 16384, 65536, 131072)):
     return best, sweep
 
 
+def measure_tf32_gemm(dev, n=8192, iters=10):
+    """cuBLAS TF32 GEMM throughput (TFLOP/s) on this GPU, measured here: the per-MMA rate the 3xTF32 kernels divide by three.
+    A library call used as a yardstick only."""
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            (a @ b)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            (a @ b)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        torch.backends.cuda.matmul.allow_tf32 = old
+        return 2.0 * n ** 3 * iters / (e0.elapsed_time(e1) * 1e-3) * 1e-12
+    except Exception:  # noqa: BLE001 - yardstick only
+        return None
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -235,7 +260,9 @@ def run_ours(args, rank, local_rank, world):
     flat = FlatGrads(net)
     n_pts_rank = sum(x.shape[0] for x in dev_groups.values())
 
-    def step(from_host=False):
+    ar_events = []          # (before, after) CUDA events around the gradient all-reduce of every timed step
+
+    def step(from_host=False, record_ar=False):
         if from_host:
             for g, x in host_groups.items():
                 dev_groups[g].copy_(x, non_blocking=True)
@@ -244,7 +271,14 @@ def run_ours(args, rank, local_rank, world):
         total = wl.combine(loss.grouped_losses("loss_type"))
         total.backward()
         if world > 1:
-            flat.all_reduce_mean()
+            if record_ar:
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record()
+                flat.all_reduce_mean()
+                eb.record()
+                ar_events.append((ea, eb))
+            else:
+                flat.all_reduce_mean()
         opt.step()
         flat.zero()
         return total
@@ -259,7 +293,7 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         e0.record()
         for _ in range(n_steps):
-            t = step(from_host)
+            t = step(from_host, record_ar=not from_host)
             if from_host:
                 t.item()          # device -> host read of the step's loss
         e1.record()
@@ -286,6 +320,45 @@ def run_ours(args, rank, local_rank, world):
         step(True).item()
     ms_e2e = timed(args.steps, from_host=True)
 
+    # per-rank record: summed kernel time of the three main kernels and the time the gradient all-reduce held the stream
+    # (wait for the slowest rank + the collective itself), gathered so that rank 0 can report min / median / max
+    ksum = 0.0
+    for k in range(3):
+        m, n = C.c_double(), C.c_int32()
+        lib.tde_profile_kind(k, C.byref(m), C.byref(n))
+        ksum += m.value
+    ar_ms = sum(a.elapsed_time(b) for a, b in ar_events)
+    mine = torch.tensor([ksum / args.steps, ar_ms / args.steps], device=dev, dtype=torch.float64)
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, mine)
+    else:
+        per_rank = [mine]
+    per_rank = torch.stack(per_rank).cpu()
+
+    graphed_ms = None
+    if args.graphed and world == 1:
+        gopt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
+
+        def graph_body():
+            out = pinn.calculate(batch)
+            total = wl.combine(losses(batch, out).grouped_losses("loss_type"))
+            total.backward()
+            gopt.step()
+            flat.zero()
+            return total
+        gstep = T.GraphedStep(graph_body)
+        for _ in range(3):
+            gstep()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(args.steps):
+            gstep()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        graphed_ms = e0.elapsed_time(e1) / args.steps
+
     if rank != 0:
         return
     n_pts_job = n_pts_rank * world
@@ -302,6 +375,7 @@ def run_ours(args, rank, local_rank, world):
     measured = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
     bf16_sustained = measured.get("bf16_tflops_sustained") or 1400.0
     tensor_peak = bf16_sustained / 2.0 / 3.0            # TF32 = bf16/2; 3xTF32 issues 3 MMAs per FP32-accurate product
+    tf32_gemm = measure_tf32_gemm(dev)                  # cuBLAS TF32 GEMM timed here, after the timed region
     tensor_src = ("3xTF32 tensor roofline = MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 rate) / 3 (three MMAs per "
                   "FP32-accurate product)" if measured else "fallback 1.4 PFLOP/s bf16 sustained / 2 / 3")
     fp32_src = "scalar-FFMA probe run in this process (tde_fp32_peak_probe); MEASURED_PEAKS.json has no FP32 entry"
@@ -334,14 +408,16 @@ def run_ours(args, rank, local_rank, world):
         k["launch_ms"] = k["ms"] / max(1, k["launches"])
         k["share_of_step"] = k["ms"] / ms_total
         del k["flops"], k["tensor"], k["ms"]
-    # DRAM bytes per point measured by `ncu --set full` at this workload (profiles/r01_tc_kernels_ncu_full_summary.csv:
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch over 510 000 points); other workloads: not captured.
-    traffic_per_point = {"jet_forward_tc_kernel": (0.009378 + 20.872160) * 1e9 / 510000,
-                         "jet_backward_tc_kernel": (20.940418 + 18.390353) * 1e9 / 510000,
-                         "jet_dw_tc_kernel": (38.728196 + 2.437561) * 1e9 / 510000} if args.workload == "ldc" else {}
+    # DRAM bytes per point and kernel: looked up in the committed table of `ncu --set full` captures
+    # (profiles/dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch / its points; the table names
+    # the capture every entry comes from).  A workload / kernel without a capture reports null.
+    traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    table = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
+    traffic_per_point = table.get("bytes_per_point", {}).get(args.workload, {})
     for k in kernels:
         per_pt = traffic_per_point.get(k["kernel"])
         k["traffic"] = per_pt * pts_total / max(1, k["launches"]) if per_pt else None
+        k["frac_vs_tf32_gemm"] = k["achieved"] / (tf32_gemm / 3.0) if k["bound"] == "tensor" and tf32_gemm else None
     dom = max(kernels, key=lambda k: k["share_of_step"])
     roofline = {"bound": dom["bound"], "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s",
                 "frac": dom["frac"], "traffic": dom["traffic"],
@@ -350,7 +426,10 @@ def run_ours(args, rank, local_rank, world):
                 "fp32_ffma_peak_probe": peak.value,
                 "step_fp32_equiv_tflops": f_pt * pts_total / (ms_total * 1e-3) * 1e-12,
                 "hbm_gbs_measured": measured.get("hbm_gbs"), "bf16_tflops_measured": measured.get("bf16_tflops"),
-                "bf16_tflops_sustained_measured": measured.get("bf16_tflops_sustained")}
+                "bf16_tflops_sustained_measured": measured.get("bf16_tflops_sustained"),
+                "tf32_gemm_tflops_here": tf32_gemm,
+                "frac_vs_tf32_gemm": dom.get("frac_vs_tf32_gemm"),
+                "traffic_source": table.get("source")}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -387,7 +466,15 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "reference_gpu": reference_gpu}
+            "reference_gpu": reference_gpu,
+            "ranks": {"kernel_sum_ms_per_step": {"min": float(per_rank[:, 0].min()), "median": float(per_rank[:, 0].median()),
+                                                 "max": float(per_rank[:, 0].max())},
+                      "allreduce_ms_per_step": {"min": float(per_rank[:, 1].min()), "median": float(per_rank[:, 1].median()),
+                                                "max": float(per_rank[:, 1].max())},
+                      "note": "all-reduce time = wait for the slowest rank + the collective, from CUDA events around it"}}
+    if graphed_ms is not None:
+        line["graphed"] = {"ms_per_step": graphed_ms, "value": n_pts_job / (graphed_ms * 1e-3), "unit": UNIT,
+                           "note": "same step replayed as one CUDA graph (torch_de_b200.GraphedStep); `value` above is the eager public API"}
     print(json.dumps(line), flush=True)
 
 

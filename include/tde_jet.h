@@ -115,6 +115,18 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
                      const float* stash, const float* seeds, int64_t ld_seeds, float grad_scale,
                      float* flat_grad, void* workspace, void* stream);
 
+/*
+ * Reverse sweep restricted to the points [p_lo, p_hi) of a forward over n_points (same x / stash / seeds buffers as
+ * tde_jet_backward; workspace of plan(n_points)).  The sweep starts at the tile that holds p_lo: the seeds of the points
+ * between that tile's first point (p_lo rounded down to a multiple of lcm(plan.tile_points, 32)) and p_lo MUST be zero.
+ * This is the building block of the fused GradNorm (utils/Loss_weighting.py:30-50 calls autograd.grad once per loss row,
+ * each a full reverse pass): a loss row only has seeds on the points of its own group, so its gradient costs a sweep over
+ * that group, not over the batch.
+ */
+int tde_jet_backward_range(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points,
+                           const float* stash, const float* seeds, int64_t ld_seeds, int64_t p_lo, int64_t p_hi,
+                           float grad_scale, float* flat_grad, void* workspace, void* stream);
+
 /* ---- fused residual assembly + loss reduction ------------------------------------------------ */
 #define TDE_OP_CONST 0  /* dst = imm                      */
 #define TDE_OP_LOAD 1   /* dst = stream[a][p]             (a = row of `streams`)                 */

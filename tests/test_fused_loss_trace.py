@@ -103,3 +103,45 @@ def test_untraceable_pieces_raise_trace_error():
     grp = T.PINN_group('g', torch.zeros(4, 1), ['x'])
     with pytest.raises(FL.TraceError):
         FL.eval_weight(L.rows[0], grp, ['u'])
+
+
+def test_tensor_scalars_are_reread_and_learnable_ones_refuse_to_fuse():
+    """A tensor scalar in a residual (annealed Re, inverse-problem coefficient) is never baked into the program."""
+    grp = T.PINN_group('g', torch.zeros(4, 1), ['x'])
+    nu = torch.tensor(0.25)
+    L = T.Loss_handler(['g'])
+    L.add_residual('g', {'r': T.DE_func(lambda u, u_x, **kw: u_x - nu * u)})
+    gp = FL.trace_group(grp, L.rows, {'u': 0, 'u_x': 1}, 2)
+    assert gp.aux_names == ['__s0'] and gp.scalars[0] is nu                 # an aux leaf, not an OP_CONST
+    assert all(gp.prog.ops[k].op != _lib.OP_CONST for k in range(gp.prog.n_ops))
+    streams = np.array([[1.0, 2.0, 3.0, 4.0], [0.5, 0.5, 0.5, 0.5]])
+    for val in (0.25, 0.125):                                                 # changed in place between "steps"
+        nu.fill_(val)
+        aux = np.stack([gp.scalars[0].reshape(1).expand(4).numpy()])
+        got = interpret(gp, streams, aux)[0]
+        assert got == pytest.approx(np.mean((0.5 - val * streams[0]) ** 2))
+    learn = torch.nn.Parameter(torch.tensor(0.1))
+    L2 = T.Loss_handler(['g'])
+    L2.add_residual('g', {'r': T.DE_func(lambda u, **kw: learn * u)})
+    with pytest.raises(FL.TraceError):
+        FL.trace_group(grp, L2.rows, {'u': 0}, 1)
+
+
+def test_signature_sees_a_changed_python_constant():
+    grp = T.PINN_group('g', torch.zeros(4, 1), ['x'])
+    box = {'re': 100.0}
+    L = T.Loss_handler(['g'])
+    L.add_residual('g', {'r': T.DE_func(lambda u, u_x, **kw: u_x - u / box['re'])})
+    gp = FL.trace_group(grp, L.rows, {'u': 0, 'u_x': 1}, 2)
+    assert FL.signature_of(grp, L.rows, {'u': 0, 'u_x': 1}) == gp.signature
+    box['re'] = 200.0
+    assert FL.signature_of(grp, L.rows, {'u': 0, 'u_x': 1}) != gp.signature
+
+
+def test_fixed_per_point_weight_tensor_is_a_weight_row():
+    grp = T.PINN_group('g', torch.zeros(4, 1), ['x'])
+    w = torch.tensor([1.0, 2.0, 3.0, 4.0])
+    L = T.Loss_handler(['g'])
+    L.add_residual('g', {'r': T.DE_func(lambda u, **kw: u)}, weighting=w)
+    got = FL.eval_weight(L.rows[0], grp, ['u'])
+    assert isinstance(got, torch.Tensor) and torch.equal(got, w)

@@ -58,7 +58,8 @@ def test_streams_loss_grads_match_reference_golden(fixture):
         # the FP64 run of the reference is the truth; FP32 reference must not be closer by more than the tolerance
         assert rel_l2(got, z['s64_' + name]) < TOL_STREAM, (name, rel_l2(got, z['s64_' + name]))
         assert max_rel(got, z['s64_' + name]) < TOL_STREAM, name
-        assert rel_l2(got, z['s32_' + name]) < TOL_STREAM, name
+        # against the reference's own float32 run: two float32 results can differ by the sum of their distances to the truth
+        assert rel_l2(got, z['s32_' + name]) < TOL_STREAM + rel_l2(z['s32_' + name], z['s64_' + name]), name
     ref_rows = dict(zip([str(r) for r in z['row_names']], z['rows64']))
     assert set(ref_rows) == set(rows)
     for k, v in rows.items():
@@ -278,8 +279,15 @@ def _oracle_case(d_in, n_out, width, n_act, ins, outs, ders, act, n_pts, seed):
     dict(d_in=2, n_out=2, width=128, n_act=5, ins=['x', 'y'], outs=['u', 'v'], ders=[], act='tanh'),                        # J=1 (value only)
     dict(d_in=2, n_out=1, width=200, n_act=3, ins=['x', 't'], outs=['u'], ders=['u_xt'], act='tanh'),                       # padded width, mixed -> J=6
     dict(d_in=2, n_out=3, width=256, n_act=3, ins=['x', 'y'], outs=['u', 'v', 'p'], ders=['u_xx', 'v_yy', 'p_x'], act='tanh'),
+    # W = 512: 8-point tiles, four neuron blocks; odd J uses the four-product MMA scheme, even J the merged + single one
+    dict(d_in=2, n_out=3, width=512, n_act=3, ins=['x', 'y'], outs=['u', 'v', 'p'], ders=['u_xx', 'v_yy', 'p_x'], act='tanh'),             # J=5
+    dict(d_in=3, n_out=3, width=512, n_act=3, ins=['x', 'y', 't'], outs=['u', 'v', 'p'], ders=['u_t', 'u_xx', 'v_yy', 'p_x'], act='tanh'),  # J=6, 2 sets
+    dict(d_in=2, n_out=1, width=512, n_act=4, ins=['x', 't'], outs=['u'], ders=['u_x', 'u_t', 'u_xx'], act='tanh'),                         # J=4, 3 sets
+    dict(d_in=1, n_out=1, width=512, n_act=3, ins=['t'], outs=['u'], ders=['u_t', 'u_tt'], act='sin'),                                      # J=3, sin
+    dict(d_in=2, n_out=2, width=512, n_act=3, ins=['x', 'y'], outs=['u', 'v'], ders=[], act='tanh'),                                        # J=1
+    dict(d_in=2, n_out=3, width=400, n_act=3, ins=['x', 'y'], outs=['u', 'v', 'p'], ders=['u_xx', 'v_yy', 'p_x'], act='tanh'),             # padded to 512
 ])
-@pytest.mark.parametrize('n_pts', [1, 17, 333])
+@pytest.mark.parametrize('n_pts', [1, 17, 333, 5000])
 def test_tensor_core_path_shapes(case, n_pts):
     pinn, out, ref, got, gref = _oracle_case(n_pts=n_pts, seed=21, **case)
     runner = pinn.deriv_method._full
@@ -287,9 +295,11 @@ def test_tensor_core_path_shapes(case, n_pts):
     from torch_de_b200 import _lib
     paths = _lib.lib().tde_plan_paths(C.byref(runner._net), C.byref(runner._spec), n_pts)
     assert paths == 3, f'expected the tcgen05 forward+backward path, got {paths}'
+    # a single point makes the norm-relative metric pointwise-relative (meaningless near a zero crossing): looser bar there
+    tol = TOL_STREAM if n_pts > 1 else 5 * TOL_STREAM
     for k in ref:
-        assert rel_l2(out[k].detach().cpu(), ref[k].detach()) < TOL_STREAM, k
-        assert max_rel(out[k].detach().cpu(), ref[k].detach()) < TOL_STREAM, k
+        assert rel_l2(out[k].detach().cpu(), ref[k].detach()) < tol, k
+        assert max_rel(out[k].detach().cpu(), ref[k].detach()) < tol, k
     assert rel_l2(got, gref) < TOL_LOSS
     assert max_rel(got, gref) < TOL_LOSS
 
@@ -436,20 +446,50 @@ def test_rwf_mlp_matches_plain_mlp_with_same_effective_weights():
         assert rel_l2(a.s.grad.cpu(), (b.weight.grad * a.v).sum(1, keepdim=True).cpu()) < 1e-5
 
 
-def test_gradnorm_weights_follow_reference_rule():
-    z, owl, params, groups = load('ldc_small')
-    wl = product_workload('ldc_small')
+@pytest.mark.parametrize('fixture', ['ldc_small', 'ldc', 'burgers'])
+def test_gradnorm_weights_follow_reference_rule(fixture):
+    """Fused GradNorm (per-row sweeps over the row's own group, tde_jet_backward_range) against the reference's rule evaluated
+    with k full autograd passes on the same forward.  ldc: tensor-core path; the groups are ragged, so every range starts and
+    ends inside a tile."""
+    z, owl, params, groups = load(fixture)
+    wl = product_workload(fixture)
     net, lins = load_net(wl, params, 'cuda')
     pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
     batch = T.make_batch(wl.input_vars, {g: x.cuda() for g, x in groups.items()})
     rows = wl.build_losses(list(groups.keys()))(batch, pinn.calculate(batch)).individual_losses()
     w0 = torch.ones(len(rows), device='cuda')
     w1 = T.GradNorm(net, w0, *rows, alpha=0.9)
+    assert T.GradNorm.last_path == 'fused'
     ps = list(net.parameters())
     mags = torch.stack([torch.sqrt(sum(g.pow(2).sum() for g in torch.autograd.grad(r, ps, retain_graph=True, allow_unused=True) if g is not None))
                         for r in rows])
     expect = 0.9 * w0 + 0.1 * (mags.sum() / mags)
     assert torch.allclose(w1, expect, rtol=1e-4)
+    # a plain tensor that does not come from the loss table takes the k-pass rule
+    T.GradNorm(net, w0[:1], rows.sum())
+    assert T.GradNorm.last_path == 'k-pass'
+
+
+def test_gradnorm_fused_path_at_scale_and_through_rwf_layers():
+    """(a) 20 011 + 3 x 1 003 ragged points on the 8x256 tensor path; (b) a Fourier_Net with RWF layers: the kernel's d/dW is
+    chained to the (v, s) leaves."""
+    from oracle import ref_autograd as O
+    owl = O.WORKLOADS['ldc']()
+    wl = WL.ldc()
+    groups = O.sample_groups(owl, 20_011, 1_003, seed=5)
+    torch.manual_seed(3)
+    for net in (wl.make_net().cuda(), T.Fourier_Net(2, 3, 128, 3, RWF=True).cuda()):
+        pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+        batch = T.make_batch(wl.input_vars, {g: x.cuda() for g, x in groups.items()})
+        rows = wl.build_losses(list(groups.keys()))(batch, pinn.calculate(batch)).individual_losses()
+        w0 = torch.ones(len(rows), device='cuda')
+        w1 = T.GradNorm(net, w0, *rows, alpha=0.5)
+        assert T.GradNorm.last_path == 'fused'
+        ps = list(net.parameters())
+        mags = torch.stack([torch.sqrt(sum(g.pow(2).sum() for g in torch.autograd.grad(r, ps, retain_graph=True, allow_unused=True) if g is not None))
+                            for r in rows])
+        expect = 0.5 * w0 + 0.5 * (mags.sum() / mags)
+        assert torch.allclose(w1, expect, rtol=2e-4), (w1, expect)
 
 
 def test_graphed_step_replays_the_eager_step_bitwise():

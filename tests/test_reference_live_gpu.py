@@ -129,6 +129,7 @@ def test_gradnorm_matches_the_reference_gradnorm_golden():
     assert torch.allclose(rows.double().cpu(), torch.from_numpy(z['rows_64']), rtol=1e-4)
     w0 = torch.from_numpy(z['w0']).float().cuda()
     w1 = T.GradNorm(net, w0, *rows)
+    assert T.GradNorm.last_path == 'fused'          # range-restricted sweeps on the shared stash, not k autograd passes
     w2 = T.GradNorm(net, w0, *rows, alpha=0.5, max_weight=50.0)
     assert torch.allclose(w1.double().cpu(), torch.from_numpy(z['w1_64']), rtol=2e-4)
     assert torch.allclose(w2.double().cpu(), torch.from_numpy(z['w2_64']), rtol=2e-4)

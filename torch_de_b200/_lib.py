@@ -49,7 +49,8 @@ class TdeLossProgram(C.Structure):
 
 EXPORTS = ["tde_last_error", "tde_version", "tde_abi_struct_bytes", "tde_plan", "tde_jet_forward", "tde_jet_backward",
            "tde_residual_loss", "tde_adam_step", "tde_fp32_peak_probe", "tde_launch_count", "tde_profile_begin",
-           "tde_profile_end", "tde_profile_kind", "tde_plan_paths", "tde_grid_interp2d", "tde_set_option"]
+           "tde_profile_end", "tde_profile_kind", "tde_plan_paths", "tde_grid_interp2d", "tde_set_option",
+           "tde_jet_backward_range"]
 
 _LIB = None
 
@@ -62,6 +63,7 @@ def _declare(lib):
     lib.tde_plan.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), i64, C.POINTER(TdePlan)]
     lib.tde_jet_forward.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), vp, i64, vp, i64, vp, vp, vp]
     lib.tde_jet_backward.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), vp, i64, vp, vp, i64, f32, vp, vp, vp]
+    lib.tde_jet_backward_range.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), vp, i64, vp, vp, i64, i64, i64, f32, vp, vp, vp]
     lib.tde_residual_loss.argtypes = [C.POINTER(TdeLossProgram), vp, i64, i32, vp, i64, i64, i64, f32, vp, vp, vp, vp, vp]
     lib.tde_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, i32, vp]
     lib.tde_fp32_peak_probe.argtypes = [C.POINTER(C.c_double), vp]

@@ -49,37 +49,42 @@ __device__ __forceinline__ void slab_add(float* dst, float v, bool first) {
     }
 }
 
-template <int NF, int SMASK, int W>
-__global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const __grid_constant__ TcBwdParams p) {
+template <int NF, int SMASK, int W, int PTS = tc_points(W, JetSpecT<NF, SMASK>::J)>
+__global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_backward_tc_kernel(const __grid_constant__ TcBwdParams p) {
     using S = JetSpecT<NF, SMASK>;
     constexpr int J = S::J;
-    constexpr int N = kTcPoints * J;
+    constexpr int N = PTS * J;
     extern __shared__ __align__(1024) unsigned char smem_tc[];
     unsigned char* const smem_raw = smem_tc;
 
     constexpr int MB = W / 128;
     constexpr int kAccSets = tc_acc_sets(MB, N);
+    constexpr int KSC = tc_ksc(W, N);
+    constexpr bool kZeroAcc = MB >= 4;           // W = 512: every MMA accumulates, the epilogue zeroes what it has read
     const int n_stages = p.n_stages;
     using P = TcPlanes<N>;
     unsigned char* zpl = smem_raw;                          // Hbar planes: [k-atom][hi | lo part][column group][8 x 128 B]
     constexpr uint32_t z_planes = (uint32_t)(W / 32) * P::kAtom;
-    const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;
+    constexpr uint32_t chunk_bytes = (uint32_t)KSC * 8192u;
     unsigned char* wst = zpl + z_planes;
     float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
-    float* xs = wout_s + p.n_out * W;                 // [16][d_in]
-    float* seeds_s = xs + kTcPoints * p.d_in;         // [16 points][J channels][4 outputs (padded)]: one float4 per point and channel
+    float* xs = wout_s + p.n_out * W;                 // [PTS][d_in]
+    float* seeds_s = xs + PTS * p.d_in;               // [PTS points][J channels][4 outputs (padded)]: one float4 per point and channel
     static_assert(TDE_MAX_OUT == 4, "seed rows are staged as float4 per channel");
     // barriers at the tail (same carve-up as the forward kernel: [planes][stages][w_out][x][seeds | y][4 floats][barriers])
-    uint64_t* full = reinterpret_cast<uint64_t*>(seeds_s + J * TDE_MAX_OUT * kTcPoints + 4);
+    uint64_t* full = reinterpret_cast<uint64_t*>(seeds_s + J * TDE_MAX_OUT * PTS + 4);
     uint64_t* empty = full + kTcMaxStages;
     uint64_t* act_ready = empty + kTcMaxStages;
-    uint64_t* acc_ready = act_ready + 2;     // [neuron block]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
+    uint64_t* acc_ready = act_ready + kTcMaxBlocks;     // [neuron block]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + kTcMaxBlocks);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int n_epi_warps = 8 * MB;
-    constexpr int n_epi = 256 * MB;
-    const int n_ks = W / kTcKC;
+    constexpr bool kTurn = tc_turn(W);           // every epilogue warp serves the neuron blocks in turn (see tc_turn)
+    constexpr int PPV = tc_visit_points(W, PTS);      // points per thread and block visit
+    constexpr int n_epi_warps = tc_epi_warps(W, PTS);
+    constexpr int n_epi = 32 * n_epi_warps;
+    constexpr int kArrivals = kTurn ? n_epi_warps : 4 * (PTS / PPV);     // epilogue warps that publish a neuron block
+    constexpr int n_ks = (int)((2u * W * W * 4u) / chunk_bytes);      // weight chunks per layer
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
             mbar_init(&empty[s], kTcCluster);
         }
         for (int b = 0; b < MB; ++b) {
-            mbar_init(&act_ready[b], 8);     // the eight epilogue warps of neuron block b
+            mbar_init(&act_ready[b], kArrivals);     // the epilogue warps that write neuron block b's adjoints
             mbar_init(&acc_ready[b], 1);
         }
         mbar_fence_init();
@@ -135,31 +140,49 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
             const uint32_t stage_step = chunk_bytes >> 4;
             int s = 0;
             uint32_t ph = 0, act_ph = 0;
-            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step)
-                for (int l = p.L - 1; l >= 1; --l)
-                    tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, a0, b0, stage_step, full, empty, act_ready, acc_ready,
-                                                    n_stages, s, ph, act_ph);
+            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
+                for (int l = p.L - 1; l >= 1; --l) {
+                    if constexpr (MB >= 4)
+                        tc_issue_layer_wide<MB, N, kAccSets, KSC>(leader, tmem_base, a0, b0, stage_step, full, empty, act_ready, acc_ready,
+                                                                  n_stages, s, ph, act_ph);
+                    else
+                        tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, a0, b0, stage_step, full, empty, act_ready, acc_ready,
+                                                        n_stages, s, ph, act_ph);
+                }
+            }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tc_epi_regs(W)));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tc_epi_regs(tc_threads(W, PTS))));
         const int e = warp - 4;
         if (e < n_epi_warps) {
             const int quarter = warp & 3;
-            const int mb = (e >> 2) % MB;            // neuron block
-            const int ph = (e >> 2) / MB;            // point half: this thread handles points 8*ph .. 8*ph+7 of every tile
-            const int n = mb * 128 + quarter * 32 + lane;   // the neuron this thread owns (in every layer)
+            const int own_mb = kTurn ? 0 : (e >> 2) % MB;     // neuron block (turn mode: the first one visited)
+            const int pg = kTurn ? (e >> 2) : (e >> 2) / MB;  // point group: this thread handles points PPV*pg .. PPV*pg+PPV-1 of every tile
+            constexpr int n_visits = kTurn ? MB : 1;          // neuron blocks a thread serves per layer
+            if constexpr (kZeroAcc) {                // all accumulator columns of my lane start at zero (every MMA accumulates)
+                tmem_zero_cols<kAccSets * N>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(own_mb * kAccSets * N));
+                tmem_wait_st();
+            }
+            const int n0 = own_mb * 128 + quarter * 32 + lane;   // the neuron this thread owns in every layer (turn mode: + 128 per visit)
             const int et = e * 32 + lane;
             auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory"); };
 
             for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
-            const uint32_t hoff = P::template hi_off<kAccSets>((uint32_t)n >> 5);
-            const uint32_t zrow = (uint32_t)(n >> 5) * P::kAtom + hoff + (uint32_t)(n & 3) * 4u;
+            const uint32_t hoff = P::template hi_off<kAccSets>((uint32_t)n0 >> 5);
+            const uint32_t zrow = (uint32_t)(n0 >> 5) * P::kAtom + hoff + (uint32_t)(n0 & 3) * 4u;
             const uint32_t lo_delta = P::kHalf - 2u * hoff;
-            const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;
-            // the two threads of a neuron (one per point half) add into separate copies of the small gradient sections
+            const uint32_t kchunk = (uint32_t)(n0 >> 2) & 7u;
+            // shared address of (column = first column of my point group + j, k = n0) in the hi part (see the forward kernel)
+            uint32_t zaddr0[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t cb = (uint32_t)(pg * PPV * J + j);
+                zaddr0[j] = smem_u32(zpl) + zrow + (cb >> 3) * 1024u + (cb & 7u) * 128u + ((kchunk ^ (cb & 7u)) << 4);
+            }
+            // the threads of a neuron (one per point group) add into separate copies of the small gradient sections
             float* gp = p.gpart + (size_t)blockIdx.x * p.gp_stride;
-            float* gp_lo = gp + p.gp_dup_lo[ph];      // w_in | b_in
-            float* gp_hi = gp + p.gp_dup_hi[ph];      // b_hidden | w_out
+            float* gp_lo = gp + p.gp_dup_lo[pg];      // w_in | b_in
+            float* gp_hi = gp + p.gp_dup_hi[pg];      // b_hidden | w_out
             uint32_t acc_ph = 0;
 
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
@@ -167,22 +190,22 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                 // the second tile of the last pair may be padding (>= n_tiles): x = 0 and seeds = 0 there and the streams have
                 // rows for it, so it runs the same code and contributes exact zeros
                 const int64_t tile = pair * kTcCluster + crank;
-                const int64_t pbase = tile * kTcPoints;
+                const int64_t pbase = tile * PTS;
                 const bool tstamp = p.dbg_buf && blockIdx.x == 0 && et == 0 && pair == first_pair + 3 * pair_step;
                 if (tstamp) p.dbg_buf[40] = clock64();      // tile start
-                for (int i = et; i < kTcPoints * p.d_in; i += n_epi) {
+                for (int i = et; i < PTS * p.d_in; i += n_epi) {
                     const int64_t gpt = pbase + i / p.d_in;
                     xs[i] = gpt < p.B ? p.x[gpt * p.d_in + (i % p.d_in)] : 0.0f;
                 }
-                for (int i = et; i < J * TDE_MAX_OUT * kTcPoints; i += n_epi) {       // coalesced over the 16 points of a seed row
-                    const int r = i / kTcPoints, pt = i - r * kTcPoints;          // r = channel * 4 + output
+                for (int i = et; i < J * TDE_MAX_OUT * PTS; i += n_epi) {       // coalesced over the points of a seed row
+                    const int r = i / PTS, pt = i - r * PTS;          // r = channel * 4 + output
                     const int c = r >> 2, o = r & 3;
                     const int64_t gpt = pbase + pt;
                     seeds_s[(pt * J + c) * 4 + o] = (o < p.n_out && gpt < p.B) ? p.seeds[(size_t)(c * p.n_out + o) * p.ld_seeds + gpt] : 0.0f;
                 }
                 epi_sync();
                 if (tstamp) p.dbg_buf[41] = clock64();      // inputs staged
-                const size_t row0 = ((size_t)tile * N + (size_t)ph * (8 * J)) * W + n;     // [layer][tile][jet column][neuron]
+                const size_t row0 = ((size_t)tile * N + (size_t)pg * (PPV * J)) * W + n0;     // [layer][tile][jet column][neuron]
 
                 // Epilogue as 2 x (2 steps of 4 points): 8 points are unrolled so every shared/global offset is an immediate (a
                 // 16-point unroll is >200 KB of code and instruction-cache bound).  The stash values of the NEXT 4-point step
@@ -190,9 +213,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                 // Base addresses pass through empty asm statements: otherwise the compiler, short of registers, re-derives
                 // every one of the 240 addresses of a layer from the kernel parameters (10 instructions per store).
                 constexpr int GC = kTcGroup * J;
-                float wo[TDE_MAX_OUT];
-#pragma unroll
-                for (int o = 0; o < TDE_MAX_OUT; ++o) wo[o] = o < p.n_out ? wout_s[o * W + n] : 0.0f;
+                constexpr int NG2 = PPV / kTcGroup;       // 4-point steps per visit
 
                 // The body is instantiated three times (last hidden layer: adjoint seeded from the output layer; middle layers;
                 // input layer) so the hot middle-layer code carries none of the special-case registers or branches.
@@ -200,136 +221,157 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                     constexpr int KIND = decltype(kind_c)::value;     // 2 last, 1 middle, 0 input layer
                     constexpr bool last = KIND == 2;
                     const size_t loff = (size_t)l * p.stash_layer_stride + row0;
-                    const float* srow_h = p.stash + loff;
-                    float* hrow_h = p.hbar + loff;
-                    uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        zaddr[j] = smem_u32(zpl) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph * (uint32_t)(J * 1024);
-                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && ph == 0 && pair == first_pair + 3 * pair_step && l >= 3 && l <= 5;
-                    long long* const dst = p.dbg_buf + 16 + ((5 - l) * 2 + mb) * 4;   // steady-state tile, both neuron blocks
-                    if (stamp) dst[0] = clock64();
-                    // all of this thread's stash values of the layer are requested before the wait for the accumulators, so their
-                    // latency hides under the MMAs (a later prefetch would share a scoreboard with younger loads and stall)
-                    float stv[2][GC];
-#pragma unroll
-                    for (int g = 0; g < 2; ++g)
-#pragma unroll
-                        for (int i = 0; i < GC; ++i) stv[g][i] = __ldcs(srow_h + (size_t)(g * GC + i) * W);
-                    uint32_t taddr = 0;
-                    if (!last) {
-                        mbar_wait_park(&acc_ready[mb], acc_ph);
-                        acc_ph ^= 1;
-                        tc_fence_after();
-                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * kAccSets * N + ph * 2 * GC);
-                    }
-                    if (stamp) dst[1] = clock64();
-                    float db = 0.0f;
-                    float dwo[TDE_MAX_OUT], dw_in[TDE_MAX_IN], dh_first[NF > 0 ? NF : 1];
-#pragma unroll
-                    for (int a = 0; a < (NF > 0 ? NF : 1); ++a) dh_first[a] = 0.0f;
-#pragma unroll
-                    for (int o = 0; o < TDE_MAX_OUT; ++o) dwo[o] = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < TDE_MAX_IN; ++i) dw_in[i] = 0.0f;
-                    const float* xs_h = xs + ph * 8 * p.d_in;
-                    const float4* seeds_h = reinterpret_cast<const float4*>(seeds_s) + ph * 8 * J;     // [point][channel]
+                    // all of this thread's stash values of the layer (every visit) are requested before the wait for the
+                    // accumulators, so their latency hides under the MMAs (a later prefetch would share a scoreboard with younger
+                    // loads and stall)
+                    float stv[n_visits][NG2][GC];
                     {
-                        asm volatile("" : "+l"(srow_h), "+l"(hrow_h));
+                        const float* srow = p.stash + loff;
+                        asm volatile("" : "+l"(srow));
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
+                        for (int v = 0; v < n_visits; ++v)
 #pragma unroll
-                        for (int g2 = 0; g2 < 2; ++g2) {
-                            float zbg[GC];
-                            const float (&stg)[GC] = stv[g2];
-                            if (!last) {
-                                // one accumulator set at a time: at most 2 x GC registers in flight next to the stash values
-                                tmem_ld_cols<GC>(taddr + (uint32_t)(g2 * GC), zbg);
-                                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            for (int g = 0; g < NG2; ++g)
 #pragma unroll
-                                for (int a = 1; a < kAccSets; ++a) {
-                                    float cur[GC];
-                                    tmem_ld_cols<GC>(taddr + (uint32_t)(a * N + g2 * GC), cur);
+                                for (int i = 0; i < GC; ++i) stv[v][g][i] = __ldcs(srow + (size_t)(g * GC + i) * W + v * 128);
+                    }
+                    static_for<n_visits>([&](auto v_c) {
+                        constexpr int v = decltype(v_c)::value;
+                        const int mb = own_mb + v, n = n0 + v * 128;
+                        float* hrow_h = p.hbar + loff + v * 128;
+                        uint32_t zaddr[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) zaddr[j] = zaddr0[j] + (uint32_t)v * 4u * P::kAtom;
+                        const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && pg == 0 && pair == first_pair + 3 * pair_step && l >= 3 && l <= 5;
+                        long long* const dst = p.dbg_buf + 16 + ((5 - l) * 2 + (mb & 1)) * 4;   // steady-state tile, two neuron blocks
+                        if (stamp) dst[0] = clock64();
+                        float wo[TDE_MAX_OUT];
+                        if (last) {
+#pragma unroll
+                            for (int o = 0; o < TDE_MAX_OUT; ++o) wo[o] = o < p.n_out ? wout_s[o * W + n] : 0.0f;
+                        }
+                        uint32_t taddr = 0;
+                        if (!last) {
+                            mbar_wait_park(&acc_ready[mb], acc_ph);
+                            tc_fence_after();
+                            taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * kAccSets * N + pg * PPV * J);
+                        }
+                        if (stamp) dst[1] = clock64();
+                        float db = 0.0f;
+                        float dwo[TDE_MAX_OUT], dw_in[TDE_MAX_IN], dh_first[NF > 0 ? NF : 1];
+#pragma unroll
+                        for (int a = 0; a < (NF > 0 ? NF : 1); ++a) dh_first[a] = 0.0f;
+#pragma unroll
+                        for (int o = 0; o < TDE_MAX_OUT; ++o) dwo[o] = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < TDE_MAX_IN; ++i) dw_in[i] = 0.0f;
+                        const float* xs_h = xs + pg * PPV * p.d_in;
+                        const float4* seeds_h = reinterpret_cast<const float4*>(seeds_s) + pg * PPV * J;     // [point][channel]
+                        {
+                            asm volatile("" : "+l"(hrow_h));
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
+#pragma unroll
+                            for (int g2 = 0; g2 < NG2; ++g2) {
+                                float zbg[GC];
+                                const float (&stg)[GC] = stv[v][g2];
+                                if (!last) {
+                                    // one accumulator set at a time: at most 2 x GC registers in flight next to the stash values
+                                    tmem_ld_cols<GC>(taddr + (uint32_t)(g2 * GC), zbg);
                                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                                    for (int i = 0; i < GC; ++i) zbg[i] += cur[i];
-                                }
-                            }
+                                    for (int a = 1; a < kAccSets; ++a) {
+                                        float cur[GC];
+                                        tmem_ld_cols<GC>(taddr + (uint32_t)(a * N + g2 * GC), cur);
+                                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                            for (int q = 0; q < kTcGroup; ++q) {
-                                const int pt8 = g2 * kTcGroup + q;      // compile-time 0..7
-                                float st[J], zb[J], hb[J], z[J];
-#pragma unroll
-                                for (int c = 0; c < J; ++c) st[c] = stg[q * J + c];
-                                float4 sd[last ? J : 1];       // seeds of this point: [channel] x 4 outputs (0 beyond n_out)
-                                if (last) {
-#pragma unroll
-                                    for (int c = 0; c < J; ++c) {
-                                        sd[c] = seeds_h[pt8 * J + c];
-                                        zb[c] = fmaf(wo[0], sd[c].x, fmaf(wo[1], sd[c].y, fmaf(wo[2], sd[c].z, wo[3] * sd[c].w)));
+                                        for (int i = 0; i < GC; ++i) zbg[i] += cur[i];
                                     }
-                                } else {
+                                    if constexpr (kZeroAcc) {
 #pragma unroll
-                                    for (int c = 0; c < J; ++c) zb[c] = zbg[q * J + c];
-                                }
-                                act_backward<S, last>(layer_act(p.act, p.fourier_half, l, n), st, zb, hb, z);     // Z_l was written by the forward pass
-                                db += hb[0];
-                                if (last) {
-#pragma unroll
-                                    for (int c = 0; c < J; ++c) {
-                                        dwo[0] = fmaf(sd[c].x, z[c], dwo[0]);
-                                        dwo[1] = fmaf(sd[c].y, z[c], dwo[1]);
-                                        dwo[2] = fmaf(sd[c].z, z[c], dwo[2]);
-                                        dwo[3] = fmaf(sd[c].w, z[c], dwo[3]);
+                                        for (int a = 0; a < kAccSets; ++a) tmem_zero_cols<GC>(taddr + (uint32_t)(a * N + g2 * GC));
                                     }
                                 }
-                                if constexpr (KIND >= 1) {
 #pragma unroll
-                                    for (int c = 0; c < J; ++c) {
-                                        const int col8 = pt8 * J + c;
-                                        __stcs(hrow_h + (size_t)col8 * W, hb[c]);
-                                        float hi, lo;
-                                        split_tf32(hb[c], hi, lo);
-                                        const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
-                                        sts_f32(a, hi);
-                                        sts_f32(a + lo_delta, lo);
+                                for (int q = 0; q < kTcGroup; ++q) {
+                                    const int pt8 = g2 * kTcGroup + q;      // compile-time 0..PPV-1
+                                    float st[J], zb[J], hb[J], z[J];
+#pragma unroll
+                                    for (int c = 0; c < J; ++c) st[c] = stg[q * J + c];
+                                    float4 sd[last ? J : 1];       // seeds of this point: [channel] x 4 outputs (0 beyond n_out)
+                                    if (last) {
+#pragma unroll
+                                        for (int c = 0; c < J; ++c) {
+                                            sd[c] = seeds_h[pt8 * J + c];
+                                            zb[c] = fmaf(wo[0], sd[c].x, fmaf(wo[1], sd[c].y, fmaf(wo[2], sd[c].z, wo[3] * sd[c].w)));
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int c = 0; c < J; ++c) zb[c] = zbg[q * J + c];
                                     }
-                                } else {
-                                    // input layer: h = W0 x + b0, h_a = W0[:, first_in[a]]
-                                    const float h0 = hb[0];
+                                    act_backward<S, last>(layer_act(p.act, p.fourier_half, l, n), st, zb, hb, z);     // Z_l was written by the forward pass
+                                    db += hb[0];
+                                    if (last) {
 #pragma unroll
-                                    for (int i = 0; i < TDE_MAX_IN; ++i)
-                                        if (i < p.d_in) dw_in[i] = fmaf(h0, xs_h[pt8 * p.d_in + i], dw_in[i]);
+                                        for (int c = 0; c < J; ++c) {
+                                            dwo[0] = fmaf(sd[c].x, z[c], dwo[0]);
+                                            dwo[1] = fmaf(sd[c].y, z[c], dwo[1]);
+                                            dwo[2] = fmaf(sd[c].z, z[c], dwo[2]);
+                                            dwo[3] = fmaf(sd[c].w, z[c], dwo[3]);
+                                        }
+                                    }
+                                    if constexpr (KIND >= 1) {
 #pragma unroll
-                                    for (int a = 0; a < NF; ++a) dh_first[a] += hb[1 + a];     // d/dW0[n][first_in[a]], added once below
+                                        for (int c = 0; c < J; ++c) {
+                                            const int col8 = pt8 * J + c;
+                                            __stcs(hrow_h + (size_t)col8 * W, hb[c]);
+                                            float hi, lo;
+                                            split_tf32(hb[c], hi, lo);
+                                            const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
+                                            sts_f32(a, hi);
+                                            sts_f32(a + lo_delta, lo);
+                                        }
+                                    } else {
+                                        // input layer: h = W0 x + b0, h_a = W0[:, first_in[a]]
+                                        const float h0 = hb[0];
+#pragma unroll
+                                        for (int i = 0; i < TDE_MAX_IN; ++i)
+                                            if (i < p.d_in) dw_in[i] = fmaf(h0, xs_h[pt8 * p.d_in + i], dw_in[i]);
+#pragma unroll
+                                        for (int a = 0; a < NF; ++a) dh_first[a] += hb[1 + a];     // d/dW0[n][first_in[a]], added once below
+                                    }
                                 }
                             }
                         }
-                    }
-                    if (stamp) dst[2] = clock64();
-                    if constexpr (KIND >= 1) {
-                        fence_proxy_async();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&act_ready[mb]);
-                        if (stamp) dst[3] = clock64();
-                        slab_add(gp_hi + p.gp_off_b_hidden + (size_t)(l - 1) * W + n, db, first);
-                    } else {
-                        slab_add(gp_lo + p.gp_off_b_in + n, db, first);
+                        if (stamp) dst[2] = clock64();
+                        if constexpr (kZeroAcc) {
+                            if (!last) tmem_wait_st();
+                        }
+                        if constexpr (KIND >= 1) {
+                            fence_proxy_async();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&act_ready[mb]);
+                            if (stamp) dst[3] = clock64();
+                            slab_add(gp_hi + p.gp_off_b_hidden + (size_t)(l - 1) * W + n, db, first);
+                        } else {
+                            slab_add(gp_lo + p.gp_off_b_in + n, db, first);
 #pragma unroll
-                        for (int a = 0; a < NF; ++a)
+                            for (int a = 0; a < NF; ++a)
+#pragma unroll
+                                for (int i = 0; i < TDE_MAX_IN; ++i)
+                                    if (i == p.first_in[a]) dw_in[i] += dh_first[a];
 #pragma unroll
                             for (int i = 0; i < TDE_MAX_IN; ++i)
-                                if (i == p.first_in[a]) dw_in[i] += dh_first[a];
+                                if (i < p.d_in) slab_add(gp_lo + (size_t)n * p.d_in + i, dw_in[i], first);
+                        }
+                        if (last) {
 #pragma unroll
-                        for (int i = 0; i < TDE_MAX_IN; ++i)
-                            if (i < p.d_in) slab_add(gp_lo + (size_t)n * p.d_in + i, dw_in[i], first);
-                    }
-                    if (last) {
-#pragma unroll
-                        for (int o = 0; o < TDE_MAX_OUT; ++o)
-                            if (o < p.n_out) slab_add(gp_hi + p.gp_off_w_out + (size_t)o * W + n, dwo[o], first);
-                    }
+                            for (int o = 0; o < TDE_MAX_OUT; ++o)
+                                if (o < p.n_out) slab_add(gp_hi + p.gp_off_w_out + (size_t)o * W + n, dwo[o], first);
+                        }
+                    });
+                    if (!last) acc_ph ^= 1;
                 };
                 layer_body(std::integral_constant<int, 2>{}, p.L - 1);
                 if (tstamp) p.dbg_buf[45] = clock64();      // last hidden layer's adjoint (from the seeds) published
@@ -341,7 +383,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_backward_tc_kernel(const
                 if (tstamp) p.dbg_buf[48] = clock64();      // input layer done
                 if (et < p.n_out) {
                     float s = 0.0f;
-                    for (int pt = 0; pt < kTcPoints; ++pt) s += seeds_s[(pt * J) * 4 + et];   // channel 0, output et
+                    for (int pt = 0; pt < PTS; ++pt) s += seeds_s[(pt * J) * 4 + et];   // channel 0, output et
                     slab_add(gp + p.gp_off_b_out + et, s, first);
                 }
                 epi_sync();   // xs / seeds_s are rewritten by the next tile
@@ -368,7 +410,10 @@ constexpr int kDwFlushTiles = 24;     // accumulator is flushed to the slab afte
 
 struct TcDwParams {
     int64_t n_tiles;                  // 16-point tiles
-    int L, W, MB, J;
+    int L, W, MB, J;                  // W: rows (n) and columns (k) of the dW block one CTA accumulates (<= 256: 512 TMEM columns)
+    int Wr;                           // neurons per jet column in the streams (the layer width); Wr = n_split * W
+    int n_split;                      // 1, or 2: W = 512 is worked as 2 x 2 quadrants (n half, k half) of 256 x 256, CTA b takes
+                                      // quadrant b % 4 and the tiles (b / 4), (b / 4) + gridDim / 4, ...
     const float* hbar;                // [L][tile][cols][W]
     const float* stash;               // forward stash (t | h_c), same layout: Z_{l-1} is recomputed from it
     int act, fourier_half;
@@ -435,8 +480,12 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tiles of this CTA: blockIdx.x, + gridDim.x, ...   (every CTA has at least one)
-    const int64_t my_tiles = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    // tiles of this CTA: group, group + n_groups, ...   (every CTA has at least one); quadrant (n half, k half) of the layer
+    const int n_quads = p.n_split * p.n_split;
+    const int quad = (int)blockIdx.x % n_quads, group = (int)blockIdx.x / n_quads, n_groups = (int)gridDim.x / n_quads;
+    const int n0 = (quad / p.n_split) * W, k0 = (quad % p.n_split) * W;       // first Hbar neuron / first Z neuron of my quadrant
+    const int Wr = p.Wr;
+    const int64_t my_tiles = (p.n_tiles - group + n_groups - 1) / n_groups;
 
     if (warp < 4) {
         if (tid == 0) {
@@ -444,17 +493,26 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
             int r = 0;
             uint32_t rph = 0;
             for (int l = 1; l < p.L; ++l) {
-                const float* hsrc = p.hbar + (size_t)l * p.stash_layer_stride;
-                const float* zsrc = p.stash + (size_t)(l - 1) * p.stash_layer_stride;
+                const float* hsrc = p.hbar + (size_t)l * p.stash_layer_stride + n0;
+                const float* zsrc = p.stash + (size_t)(l - 1) * p.stash_layer_stride + k0;
                 for (int64_t t = 0; t < my_tiles; ++t) {
-                    const int64_t tile = blockIdx.x + t * gridDim.x;
-                    const size_t base = (size_t)tile * N * W;
+                    const int64_t tile = group + t * n_groups;
+                    const size_t base = (size_t)tile * N * Wr;
                     for (int ks = 0; ks < n_ks; ++ks) {
                         mbar_wait(&raw_empty[r], rph ^ 1);
                         mbar_expect_tx(&raw_full[r], raw_bytes);
                         unsigned char* dst = raws + (size_t)r * raw_bytes;
-                        bulk_g2s(dst, hsrc + base + (size_t)ks * 8 * W, op_bytes, &raw_full[r]);
-                        bulk_g2s(dst + op_bytes, zsrc + base + (size_t)ks * 8 * W, op_bytes, &raw_full[r]);
+                        if (Wr == W) {        // 8 columns of W neurons are one contiguous segment
+                            bulk_g2s(dst, hsrc + base + (size_t)ks * 8 * W, op_bytes, &raw_full[r]);
+                            bulk_g2s(dst + op_bytes, zsrc + base + (size_t)ks * 8 * W, op_bytes, &raw_full[r]);
+                        } else {              // my W of the column's Wr neurons: one segment per column
+                            const uint32_t seg = (uint32_t)W * 4u;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                bulk_g2s(dst + c * seg, hsrc + base + (size_t)(ks * 8 + c) * Wr, seg, &raw_full[r]);
+                                bulk_g2s(dst + op_bytes + c * seg, zsrc + base + (size_t)(ks * 8 + c) * Wr, seg, &raw_full[r]);
+                            }
+                        }
                         if (++r == kDwRaw) {
                             r = 0;
                             rph ^= 1;
@@ -568,7 +626,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) jet_dw_tc_kernel(const __grid_c
                         }
                     } else {
                         // stash side: 8 points = 8 J columns = J k-steps at a time: (t | h_c) -> Z jets of layer l-1, neuron n
-                        const int actn = layer_act(p.act, p.fourier_half, l - 1, n);
+                        const int actn = layer_act(p.act, p.fourier_half, l - 1, k0 + n);
                         for (int j = 0; j < total; j += J) {
                             // every output k-step is emitted as soon as the points that touch its 8 columns are converted:
                             // reads, conversions and emits interleave (all indices compile-time) instead of J reads, 8

@@ -21,13 +21,29 @@ namespace tde {
 constexpr int kTcPoints = 16;      // points per tile
 constexpr int kTcKC = 8;           // k rows per weight chunk (= one tf32 MMA K step)
 constexpr int kTcMaxStages = 8;
-constexpr int kTcTailBytes = 4 * 4 + (2 * kTcMaxStages + 4) * 8 + 16;   // b_out copy, barriers, TMEM slot   // weight stages of the tensor-core kernels (as many as shared memory allows)
-// 4 control warps + 8 epilogue warps per 128-neuron block: a warp may only read the TMEM lanes 32*(warp%4)..+31, so every
-// lane quarter gets two warps, one per half of the tile's 16 points
-__host__ __device__ constexpr int tc_threads(int W) { return 128 + 256 * (W / 128); }
+constexpr int kTcMaxBlocks = 4;     // 128-neuron blocks per layer (W <= 512)
+constexpr int kTcTailBytes = 4 * 4 + (2 * kTcMaxStages + 2 * kTcMaxBlocks) * 8 + 16;   // b_out copy, barriers, TMEM slot   // weight stages of the tensor-core kernels (as many as shared memory allows)
+// Epilogue warps.  A warp may only read the TMEM lanes 32*(warp%4)..+31, so every lane quarter gets the same number of warps.
+//   W <= 256 ("turn" mode): 16 warps = 4 lane quarters x 4 groups of 4 points; EVERY warp serves the neuron blocks in turn
+//            (block 0's accumulators, then block 1's), so a block's epilogue is done by all sixteen warps in half the time of
+//            eight warps owning it -- the next layer's first MMAs wait for exactly that epilogue (period max(4Q, 3Q + E)).
+//   W = 512: 16 warps = 4 blocks x 4 lane quarters, each owns one neuron block and the 8 points of the (8-point) tile.
+__host__ __device__ constexpr bool tc_turn(int W) { return W <= 256; }
+__host__ __device__ constexpr int tc_visit_points(int W, int pts) { return tc_turn(W) || pts < 8 ? 4 : 8; }     // points per thread and block visit
+__host__ __device__ constexpr int tc_epi_warps(int W, int pts) {
+    return tc_turn(W) ? 4 * (pts / tc_visit_points(W, pts)) : 4 * (W / 128) * (pts / tc_visit_points(W, pts));
+}
+// 4 control warps + the epilogue warps
+__host__ __device__ constexpr int tc_threads(int W, int pts = 16) { return 128 + 32 * tc_epi_warps(W, pts); }
 // registers per epilogue thread after setmaxnreg (control warps keep 24).  The pool is what the CTA was launched with:
 // 640 threads x 96 registers, so (61440 - 128*24) / 512 = 114 -> 112; asking for more blocks forever
-__host__ __device__ constexpr int tc_epi_regs(int W) { return W == 256 ? 112 : 232; }
+__host__ __device__ constexpr int tc_epi_regs(int threads) { return threads == 640 ? 112 : 232; }
+// points per tile: the activation planes of a tile (W x 2 x PTS*J floats) must fit shared memory next to the weight stages
+// (W = 512: 8 points; 4 when J >= 6, so that three accumulator sets of all four neuron blocks fit the 512 TMEM columns)
+__host__ __device__ constexpr int tc_points(int W, int J) { return W >= 512 ? (J >= 6 ? 4 : 8) : 16; }
+// k-steps (8 inputs) per streamed weight chunk of one neuron block: [hi 4 KB | lo 4 KB] each.  W = 512 with 48 jet columns
+// has room for 8 KB stages only.
+__host__ __device__ constexpr int tc_ksc(int W, int n) { return W == 128 ? 1 : (W == 512 && n > 40 ? 1 : 2); }
 #ifndef TDE_TC_CLUSTER
 #define TDE_TC_CLUSTER 2
 #endif
@@ -188,6 +204,28 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {
         tmem_ld_piece<1>(taddr, v);
     }
 }
+// zero NC consecutive TMEM columns of this thread's lane (no wait: pair with tcgen05.wait::st)
+template <int NC>
+__device__ __forceinline__ void tmem_zero_cols(uint32_t taddr) {
+    const uint32_t z = 0u;
+    if constexpr (NC >= 16) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+        if constexpr (NC > 16) tmem_zero_cols<NC - 16>(taddr + 16);
+    } else if constexpr (NC >= 8) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+        if constexpr (NC > 8) tmem_zero_cols<NC - 8>(taddr + 8);
+    } else if constexpr (NC >= 4) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+        if constexpr (NC > 4) tmem_zero_cols<NC - 4>(taddr + 4);
+    } else if constexpr (NC >= 2) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+        if constexpr (NC > 2) tmem_zero_cols<NC - 2>(taddr + 2);
+    } else if constexpr (NC == 1) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(z) : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // One layer's GEMM, issued by the converged MMA warp (one elected lane issues, the whole warp runs the control flow: a
 // tcgen05.mma inside divergent code is wrapped by the compiler in an ELECT/branch loop of ~100 cycles each).
 //
@@ -314,21 +352,102 @@ __device__ __forceinline__ void tc_issue_layer(const bool leader, const uint32_t
     act_ph ^= 1;
 }
 
-constexpr int kTcGroup = 4;        // points handled per unrolled epilogue step (16 points = 4 steps)
 // accumulator sets that fit the 512 TMEM columns (3: cross terms | main even k-steps | main odd k-steps)
 #ifndef TDE_MAX_ACC_SETS
 #define TDE_MAX_ACC_SETS 3
 #endif
 __host__ __device__ constexpr int tc_acc_sets(int mb, int n) { return 512 / (mb * n) >= TDE_MAX_ACC_SETS ? TDE_MAX_ACC_SETS : 512 / (mb * n); }
-// the single-CTA kernels need a cross-term set (>= 2) and a merged MMA of N = 2 x 16 J <= 256 columns
-__host__ __device__ constexpr bool tc_shape_ok(int mb, int n) { return 2 * n <= 256 && tc_acc_sets(mb, n) >= 2; }
+// An M = 128 MMA takes N in multiples of 16.  A tile of 8 J columns with odd J (N = 8, 24, 40) therefore only has the merged
+// 2N-wide MMA: both weight parts multiply [B_hi | B_lo] ("four products", the lo*lo term lands in the idle main set of the
+// k-atom), which needs all three accumulator sets.
+__host__ __device__ constexpr bool tc_four_products(int n) { return n % 16 != 0; }
+// the single-CTA kernels need a cross-term set (>= 2) and a merged MMA of N = 2 x PTS J <= 256 columns
+// W = 512 (mb = 4) always runs three sets: with two, every pre-activation is ONE chain of 64 round-toward-zero accumulations
+// and ten layers of that put u_xx 1.0e-5 from the float64 reference (measured on the unsteady cylinder, J = 6, 8-point
+// tiles); J = 6 therefore works 4-point tiles there (tc_points)
+__host__ __device__ constexpr bool tc_shape_ok(int mb, int n) {
+    if (mb >= 4) return n % 8 == 0 && 2 * n <= 256 && tc_acc_sets(mb, n) == 3;
+    return 2 * n <= 256 && (tc_four_products(n) ? tc_acc_sets(mb, n) == 3 : tc_acc_sets(mb, n) >= 2);
+}
+// W = 512 (MB = 4 neuron blocks, 8- or 4-point tiles): the layer is issued as MB x MB units (k quarter kq = 128 inputs = the neurons
+// of block kq, neuron block mb), kq-major: (0,0) (1,0) (2,0) (3,0) (0,1) ...  Unit (mb, 0) needs the previous layer's epilogue of
+// block mb to have drained its accumulators and written its quarter of the planes -- one wait on act_ready[mb]; after the first
+// MB units the whole plane is known to be complete.  Block mb's accumulators are complete after unit (mb, MB-1), so its epilogue
+// runs under the remaining units of the layer and the first units of the next one: a window of MB-1 units (~3/16 of a layer).
+// The order is forced by the in-place planes: block mb's epilogue overwrites the plane rows of k quarter mb, which no later
+// unit of the layer reads (only k quarter MB-1 is still being read, and block MB-1 finishes last).  A block-major order would
+// let every block's epilogue run under the following blocks, but those still read the rows it overwrites.
+// Every MMA accumulates (the epilogue zeroes the TMEM columns it has read), so there is no first-k-step special case, and
+// the k-step loop is unrolled per unit only (k-atom parity is the unit-local one because a unit starts on an even atom).
+//   N % 16 == 0:  A_hi x [B_hi | B_lo] -> [main even | cross] resp. [cross | main odd];  A_lo x B_hi -> cross
+//   N % 16 == 8:  an M = 128 MMA cannot be N wide, only 2N: A_lo multiplies [B_hi | B_lo] too; its lo*lo half -- a legitimate
+//                 term of the exact product -- lands in the main set the k-atom does not use:
+//                 even k-atom: A_hi -> [main even | cross], A_lo -> [cross | main odd];  odd: A_hi -> [cross | main odd], A_lo -> [main even | cross]
+template <int MB, int N, int kAccSets, int KSC>
+__device__ __forceinline__ void tc_issue_layer_wide(const bool leader, const uint32_t tmem_base, const uint64_t a0, const uint64_t b0,
+                                                    const uint32_t stage_step, uint64_t* full, uint64_t* empty, uint64_t* act_ready,
+                                                    uint64_t* acc_ready, const int n_stages, int& s, uint32_t& ph, uint32_t& act_ph) {
+    using P = TcPlanes<N>;
+    constexpr bool kFour = tc_four_products(N);
+    static_assert(kAccSets == 3, "W = 512 runs three accumulator sets (tc_shape_ok)");
+    constexpr uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_lo32 = (uint32_t)a0, a_hi32 = (uint32_t)(a0 >> 32), b_lo32 = (uint32_t)b0, b_hi32 = (uint32_t)(b0 >> 32);
+    auto desc = [](const uint32_t lo, const uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
+    for (int u = 0; u < MB * MB; ++u) {
+        const int kq = u / MB, mb = u % MB;
+        if (u < MB) {
+            mbar_wait(&act_ready[u], act_ph);
+            tc_fence_after();
+        }
+        const uint32_t d = tmem_base + (uint32_t)(mb * kAccSets * N);
+        const uint32_t b_unit32 = b_lo32 + (((uint32_t)kq * 4u * P::kAtom) >> 4);       // 4 k-atoms of 32 inputs per unit
+        static_for<16 / KSC>([&](auto cc_c) {
+            constexpr int cc = decltype(cc_c)::value;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t a_stage32 = a_lo32 + (uint32_t)s * stage_step;
+                static_for<KSC>([&](auto s2_c) {
+                    constexpr int s2 = decltype(s2_c)::value, ks = cc * KSC + s2;          // k-step inside the unit
+                    constexpr uint32_t j = (uint32_t)ks >> 2;
+                    constexpr uint32_t atom = j * P::kAtom + ((uint32_t)ks & 3u) * 32u;
+                    constexpr bool odd = (j & 1u) != 0;
+                    const uint64_t a_hi = desc(a_stage32 + (uint32_t)(s2 * (8192 >> 4)), a_hi32);
+                    const uint64_t a_lo = desc(a_stage32 + (uint32_t)(s2 * (8192 >> 4)) + (4096u >> 4), a_hi32);
+                    const uint64_t b_both = desc(b_unit32 + (atom >> 4), b_hi32);        // [hi | lo], odd atoms: [lo | hi]
+                    umma_tf32(d + (odd ? N : 0), a_hi, b_both, idesc2, 1);
+                    if constexpr (kFour) {
+                        umma_tf32(d + (odd ? 0 : N), a_lo, b_both, idesc2, 1);
+                    } else {
+                        const uint64_t b_hi = desc(b_unit32 + ((atom + (odd ? P::kHalf : 0u)) >> 4), b_hi32);
+                        umma_tf32(d + N, a_lo, b_hi, idesc1, 1);
+                    }
+                });
+                umma_commit_mc(&empty[s], (uint16_t)((1u << kTcCluster) - 1));
+            }
+            __syncwarp();
+            if (++s == n_stages) {
+                s = 0;
+                ph ^= 1;
+            }
+        });
+        if (kq == MB - 1) {
+            if (leader) umma_commit(&acc_ready[mb]);
+            __syncwarp();
+        }
+    }
+    act_ph ^= 1;
+}
+
+constexpr int kTcGroup = 4;        // points handled per unrolled epilogue step (16 points = 4 steps)
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
-template <int NF, int SMASK, int W>
-__global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const __grid_constant__ TcParams p) {
+template <int NF, int SMASK, int W, int PTS = tc_points(W, JetSpecT<NF, SMASK>::J)>
+__global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_forward_tc_kernel(const __grid_constant__ TcParams p) {
     using S = JetSpecT<NF, SMASK>;
     constexpr int J = S::J;
-    constexpr int N = kTcPoints * J;             // jet columns per tile (multiple of 16)
+    constexpr int N = PTS * J;                   // jet columns per tile
     // activation planes: K-major SWIZZLE_128B atoms of 8 jet columns x 32 k (1024 B), ordered [k/32][col/8].  A warp's 32
     // consecutive neurons write one full 128 B row per column (conflict-free) and every MMA operand row is 128 B aligned.
     extern __shared__ __align__(1024) unsigned char smem_tc[];
@@ -336,27 +455,32 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
 
     constexpr int MB = W / 128;
     constexpr int kAccSets = tc_acc_sets(MB, N);
+    constexpr int KSC = tc_ksc(W, N);            // k-steps per weight chunk
+    constexpr bool kZeroAcc = MB >= 4;           // W = 512: every MMA accumulates, the epilogue zeroes what it has read
     const int n_stages = p.n_stages;
     using P = TcPlanes<N>;
     unsigned char* zpl = smem_raw;                                   // activation planes: [k-atom][hi | lo part][column group][8 x 128 B]
     constexpr uint32_t z_planes = (uint32_t)(W / 32) * P::kAtom;
-    const uint32_t chunk_bytes = (uint32_t)MB * 2u * 2u * 2048u;   // [hi|lo][mb][kgroup 2][16 row groups][8][4] floats*4
+    constexpr uint32_t chunk_bytes = (uint32_t)KSC * 8192u;         // one neuron block, KSC k-steps: [hi|lo][kgroup 2][16 row groups][8][4] floats
     unsigned char* wst = zpl + z_planes;                             // [n_stages][chunk_bytes]
     float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
-    float* xs = wout_s + p.n_out * W;            // [16][d_in]
-    float* ybuf = xs + kTcPoints * p.d_in;       // [J*n_out][16]
-    float* bout_s = ybuf + J * TDE_MAX_OUT * kTcPoints; // [4]
+    float* xs = wout_s + p.n_out * W;            // [PTS][d_in]
+    float* ybuf = xs + PTS * p.d_in;             // [J*n_out][PTS]
+    float* bout_s = ybuf + J * TDE_MAX_OUT * PTS; // [4]
     // barriers at the tail (kTcTailBytes): the planes need the 1024 B alignment of the base, a header would waste ~850 B
     uint64_t* full = reinterpret_cast<uint64_t*>(bout_s + 4);
     uint64_t* empty = full + kTcMaxStages;
     uint64_t* act_ready = empty + kTcMaxStages;
-    uint64_t* acc_ready = act_ready + 2;     // [neuron block]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 2);
+    uint64_t* acc_ready = act_ready + kTcMaxBlocks;     // [neuron block]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + kTcMaxBlocks);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int n_epi_warps = 8 * MB;
-    constexpr int n_epi = 256 * MB;
-    const int n_ks = W / kTcKC;
+    constexpr bool kTurn = tc_turn(W);           // every epilogue warp serves the neuron blocks in turn (see tc_turn)
+    constexpr int PPV = tc_visit_points(W, PTS);      // points per thread and block visit
+    constexpr int n_epi_warps = tc_epi_warps(W, PTS);
+    constexpr int n_epi = 32 * n_epi_warps;
+    constexpr int kArrivals = kTurn ? n_epi_warps : 4 * (PTS / PPV);     // epilogue warps that publish a neuron block
+    constexpr int n_chunks = (int)((2u * W * W * 4u) / chunk_bytes);      // weight chunks per layer
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
@@ -364,7 +488,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
             mbar_init(&empty[s], kTcCluster);   // one tcgen05.commit arrival from the MMA issuer of every CTA in the cluster
         }
         for (int b = 0; b < MB; ++b) {
-            mbar_init(&act_ready[b], 8);     // the eight epilogue warps of neuron block b
+            mbar_init(&act_ready[b], kArrivals);     // the epilogue warps that write neuron block b's activations
             mbar_init(&acc_ready[b], 1);
         }
         mbar_fence_init();
@@ -393,8 +517,8 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
             const uint32_t part = chunk_bytes / kTcCluster;
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
                 for (int l = 1; l < p.L; ++l) {
-                    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wc) + (size_t)(l - 1) * n_ks * chunk_bytes;
-                    for (int ks = 0; ks < n_ks; ++ks) {
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wc) + (size_t)(l - 1) * n_chunks * chunk_bytes;
+                    for (int ks = 0; ks < n_chunks; ++ks) {
                         mbar_wait(&empty[s], ph ^ 1);   // both CTAs have finished reading this stage
                         mbar_expect_tx(&full[s], chunk_bytes);      // my part + the peer's part will land here
                         bulk_g2s_mc(wst + (size_t)s * chunk_bytes + crank * part, src + (size_t)ks * chunk_bytes + crank * part, part,
@@ -420,38 +544,56 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                 for (int l = 1; l < p.L; ++l) {
                     const bool mstamp = p.dbg_buf && blockIdx.x == 0 && tile == 0 && l == 2 && lane == 0;
                     if (mstamp) p.dbg_buf[8] = clock64();
-                    tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, a0, b0, stage_step, full, empty, act_ready, acc_ready,
-                                                    n_stages, s, ph, act_ph);
+                    if constexpr (MB >= 4)
+                        tc_issue_layer_wide<MB, N, kAccSets, KSC>(leader, tmem_base, a0, b0, stage_step, full, empty, act_ready, acc_ready,
+                                                                  n_stages, s, ph, act_ph);
+                    else
+                        tc_issue_layer<MB, N, kAccSets>(leader, tmem_base, a0, b0, stage_step, full, empty, act_ready, acc_ready,
+                                                        n_stages, s, ph, act_ph);
                     if (mstamp) p.dbg_buf[10] = clock64();
                 }
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tc_epi_regs(W)));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tc_epi_regs(tc_threads(W, PTS))));
         const int e = warp - 4;                      // epilogue warp
         if (e < n_epi_warps) {
             const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-            const int mb = (e >> 2) % MB;            // neuron block
-            const int ph = (e >> 2) / MB;            // point half: this thread handles points 8*ph .. 8*ph+7 of every tile
-            const int n = mb * 128 + quarter * 32 + lane;   // the neuron this thread owns
+            const int own_mb = kTurn ? 0 : (e >> 2) % MB;     // neuron block (turn mode: the first one visited)
+            const int pg = kTurn ? (e >> 2) : (e >> 2) / MB;  // point group: this thread handles points PPV*pg .. PPV*pg+PPV-1 of every tile
+            constexpr int n_visits = kTurn ? MB : 1;          // neuron blocks a thread serves per layer
+            if constexpr (kZeroAcc) {                // all accumulator columns of my lane start at zero (every MMA accumulates)
+                tmem_zero_cols<kAccSets * N>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(own_mb * kAccSets * N));
+                tmem_wait_st();
+            }
+            const int n0 = own_mb * 128 + quarter * 32 + lane;   // the neuron this thread owns (turn mode: + 128 per visit)
             const int et = e * 32 + lane;            // 0..n_epi-1 dense index for strided loops
             auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory"); };
 
             for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
             if (et < p.n_out) bout_s[et] = p.b_out[et];
-            // byte offset of element (col, k = n) inside a Z plane
-            const uint32_t hoff = P::template hi_off<kAccSets>((uint32_t)n >> 5);
-            const uint32_t zrow = (uint32_t)(n >> 5) * P::kAtom + hoff + (uint32_t)(n & 3) * 4u;   // k-atom, hi part, byte within the 16 B chunk
+            // byte offset of element (col, k = n) inside a Z plane.  The k-atom parity (where the hi part sits), the byte inside the
+            // 16 B chunk and the chunk index depend on the lane quarter and the lane only: a visit of block v adds 4 v k-atoms.
+            const uint32_t hoff = P::template hi_off<kAccSets>((uint32_t)n0 >> 5);
+            const uint32_t zrow = (uint32_t)(n0 >> 5) * P::kAtom + hoff + (uint32_t)(n0 & 3) * 4u;   // k-atom, hi part, byte within the 16 B chunk
             const uint32_t lo_delta = P::kHalf - 2u * hoff;                                       // hi -> lo part of the same k-atom (wraps for odd atoms)
-            const uint32_t kchunk = (uint32_t)(n >> 2) & 7u;                                // 16 B chunk index before the swizzle
+            const uint32_t kchunk = (uint32_t)(n0 >> 2) & 7u;                                // 16 B chunk index before the swizzle
+            // shared address of (column = first column of my point group + j, k = n0) in the hi part, j = 0..7: column c = 8 g + j of
+            // my group is then zaddr0[j] + g * 1024 with compile-time g and j
+            uint32_t zaddr0[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t cb = (uint32_t)(pg * PPV * J + j);
+                zaddr0[j] = smem_u32(zpl) + zrow + (cb >> 3) * 1024u + (cb & 7u) * 128u + ((kchunk ^ (cb & 7u)) << 4);
+            }
             uint32_t acc_ph = 0;
 
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
                 const int64_t tile = pair * kTcCluster + crank;     // may be a padding tile (>= n_tiles, all points >= B)
-                const int64_t pbase = tile * kTcPoints;
+                const int64_t pbase = tile * PTS;
                 const bool tstamp = p.dbg_buf && blockIdx.x == 0 && et == 0 && pair == first_pair + 3 * pair_step;
                 if (tstamp) p.dbg_buf[40] = clock64();      // tile start
-                for (int i = et; i < kTcPoints * p.d_in; i += n_epi) {
+                for (int i = et; i < PTS * p.d_in; i += n_epi) {
                     const int64_t gp = pbase + i / p.d_in;
                     xs[i] = gp < p.B ? p.x[gp * p.d_in + (i % p.d_in)] : 0.0f;
                 }
@@ -459,7 +601,7 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                 if (tstamp) p.dbg_buf[41] = clock64();      // inputs staged
                 // [layer][tile][jet column][neuron]: this thread's neuron, first column of the tile.  A padding tile (the second
                 // tile of the last pair when the tile count is odd) has stash rows of its own and x = 0.
-                float* const stash_row = p.stash ? p.stash + ((size_t)tile * N + (size_t)ph * (8 * J)) * W + n : nullptr;
+                float* const stash_row = p.stash ? p.stash + ((size_t)tile * N + (size_t)pg * (PPV * J)) * W + n0 : nullptr;
 
                 // Per layer the epilogue walks the 16 points as 2 x (2 steps of 4 points): 8 points are unrolled so every
                 // shared/global offset is an immediate (a 16-point unroll is >80 KB of code and instruction-cache bound).
@@ -469,94 +611,102 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                 auto layer_body = [&](auto first_c, auto stash_c, const int l) {
                     constexpr bool kFirst = decltype(first_c)::value;     // input layer (no GEMM) vs hidden layers
                     constexpr bool kStash = decltype(stash_c)::value;
-                    float* srow_h = kStash ? stash_row + (size_t)l * p.stash_layer_stride : nullptr;
-                    uint32_t zaddr[8];      // shared address of (column & 7 == j, k = n) in the hi plane, first half
+#pragma unroll 1
+                    for (int v = 0; v < n_visits; ++v) {
+                        const int mb = own_mb + v, n = n0 + v * 128;
+                        float* srow_h = kStash ? stash_row + (size_t)l * p.stash_layer_stride + v * 128 : nullptr;
+                        uint32_t zaddr[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        zaddr[j] = smem_u32(zpl) + zrow + ((kchunk ^ (uint32_t)j) << 4) + (uint32_t)j * 128u + (uint32_t)ph * (uint32_t)(J * 1024);
-                    float wrow[TDE_MAX_IN], wf[NF > 0 ? NF : 1];
-                    float bn;
-                    uint32_t taddr = 0;
-                    const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && ph == 0 && pair == first_pair + 3 * pair_step && l >= 2 && l <= 4;
-                    long long* const dst = p.dbg_buf + 16 + ((l - 2) * 2 + mb) * 4;   // steady-state tile, both neuron blocks
-                    if (stamp) dst[0] = clock64();
-                    if constexpr (kFirst) {
+                        for (int j = 0; j < 8; ++j) zaddr[j] = zaddr0[j] + (uint32_t)v * 4u * P::kAtom;
+                        float wrow[TDE_MAX_IN], wf[NF > 0 ? NF : 1];
+                        float bn;
+                        uint32_t taddr = 0;
+                        const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && pg == 0 && pair == first_pair + 3 * pair_step && l >= 2 && l <= 4;
+                        long long* const dst = p.dbg_buf + 16 + ((l - 2) * 2 + (mb & 1)) * 4;   // steady-state tile, two neuron blocks
+                        if (stamp) dst[0] = clock64();
+                        if constexpr (kFirst) {
 #pragma unroll
-                        for (int i = 0; i < TDE_MAX_IN; ++i) wrow[i] = i < p.d_in ? __ldg(p.w_in + n * p.d_in + i) : 0.0f;
-                        bn = __ldg(p.b_in + n);
+                            for (int i = 0; i < TDE_MAX_IN; ++i) wrow[i] = i < p.d_in ? __ldg(p.w_in + n * p.d_in + i) : 0.0f;
+                            bn = __ldg(p.b_in + n);
 #pragma unroll
-                        for (int a = 0; a < NF; ++a) wf[a] = __ldg(p.w_in + n * p.d_in + p.first_in[a]);
-                    } else {
-                        bn = __ldg(p.b_hidden + (size_t)(l - 1) * W + n);
-                        mbar_wait_park(&acc_ready[mb], acc_ph);
-                        acc_ph ^= 1;
-                        tc_fence_after();
-                        taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * kAccSets * N + ph * 2 * GC);
-                    }
-                    const float* xs_h = xs + ph * 8 * p.d_in;
-                    if (stamp) dst[1] = clock64();
-                    {
-                        if constexpr (kStash) asm volatile("" : "+l"(srow_h));
+                            for (int a = 0; a < NF; ++a) wf[a] = __ldg(p.w_in + n * p.d_in + p.first_in[a]);
+                        } else {
+                            bn = __ldg(p.b_hidden + (size_t)(l - 1) * W + n);
+                            mbar_wait_park(&acc_ready[mb], acc_ph);
+                            tc_fence_after();
+                            taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mb * kAccSets * N + pg * PPV * J);
+                        }
+                        const float* xs_h = xs + pg * PPV * p.d_in;
+                        if (stamp) dst[1] = clock64();
+                        {
+                            if constexpr (kStash) asm volatile("" : "+l"(srow_h));
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
+                            for (int j = 0; j < 8; ++j) asm volatile("" : "+r"(zaddr[j]));
 #pragma unroll
-                        for (int g2 = 0; g2 < 2; ++g2) {
-                            float hg[GC];
-                            if constexpr (!kFirst) {
-                                float cur[kAccSets][GC];
+                            for (int g2 = 0; g2 < PPV / kTcGroup; ++g2) {
+                                float hg[GC];
+                                if constexpr (!kFirst) {
+                                    float cur[kAccSets][GC];
 #pragma unroll
-                                for (int a = 0; a < kAccSets; ++a) tmem_ld_cols<GC>(taddr + (uint32_t)(a * N + g2 * GC), cur[a]);
-                                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                                    for (int a = 0; a < kAccSets; ++a) tmem_ld_cols<GC>(taddr + (uint32_t)(a * N + g2 * GC), cur[a]);
+                                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                                    if constexpr (kZeroAcc) {
 #pragma unroll
-                                for (int i = 0; i < GC; ++i) {
-                                    float v = cur[0][i];
+                                        for (int a = 0; a < kAccSets; ++a) tmem_zero_cols<GC>(taddr + (uint32_t)(a * N + g2 * GC));
+                                    }
 #pragma unroll
-                                    for (int a = 1; a < kAccSets; ++a) v += cur[a][i];
-                                    hg[i] = v;
+                                    for (int i = 0; i < GC; ++i) {
+                                        float vv = cur[0][i];
+#pragma unroll
+                                        for (int a = 1; a < kAccSets; ++a) vv += cur[a][i];
+                                        hg[i] = vv;
+                                    }
                                 }
-                            }
 #pragma unroll
-                            for (int q = 0; q < kTcGroup; ++q) {
-                                const int pt8 = g2 * kTcGroup + q;          // compile-time 0..7
-                                float h[J], z[J];
-                                if constexpr (kFirst) {
-                                    float h0 = bn;
+                                for (int q = 0; q < kTcGroup; ++q) {
+                                    const int pt8 = g2 * kTcGroup + q;          // compile-time 0..PPV-1
+                                    float h[J], z[J];
+                                    if constexpr (kFirst) {
+                                        float h0 = bn;
 #pragma unroll
-                                    for (int i = 0; i < TDE_MAX_IN; ++i)
-                                        if (i < p.d_in) h0 = fmaf(wrow[i], xs_h[pt8 * p.d_in + i], h0);
-                                    h[0] = h0;
+                                        for (int i = 0; i < TDE_MAX_IN; ++i)
+                                            if (i < p.d_in) h0 = fmaf(wrow[i], xs_h[pt8 * p.d_in + i], h0);
+                                        h[0] = h0;
 #pragma unroll
-                                    for (int a = 0; a < NF; ++a) h[1 + a] = wf[a];
+                                        for (int a = 0; a < NF; ++a) h[1 + a] = wf[a];
 #pragma unroll
-                                    for (int qq = 0; qq < S::NS; ++qq) h[1 + NF + qq] = 0.0f;
-                                } else {
+                                        for (int qq = 0; qq < S::NS; ++qq) h[1 + NF + qq] = 0.0f;
+                                    } else {
 #pragma unroll
-                                    for (int c = 0; c < J; ++c) h[c] = hg[q * J + c];
-                                    h[0] += bn;
-                                }
-                                act_forward<S>(layer_act(p.act, p.fourier_half, l, n), h, z);      // h[0] now holds the value to stash (t | h0)
+                                        for (int c = 0; c < J; ++c) h[c] = hg[q * J + c];
+                                        h[0] += bn;
+                                    }
+                                    act_forward<S>(layer_act(p.act, p.fourier_half, l, n), h, z);      // h[0] now holds the value to stash (t | h0)
 #pragma unroll
-                                for (int c = 0; c < J; ++c) {
-                                    const int col8 = pt8 * J + c;           // column within this half (compile-time)
-                                    if constexpr (kStash) __stcs(srow_h + (size_t)col8 * W, h[c]);      // one 128 B line per warp store
-                                    float hi, lo;
-                                    split_tf32(z[c], hi, lo);
-                                    const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
-                                    sts_f32(a, hi);
-                                    sts_f32(a + lo_delta, lo);
+                                    for (int c = 0; c < J; ++c) {
+                                        const int col8 = pt8 * J + c;           // column within my point group (compile-time)
+                                        if constexpr (kStash) __stcs(srow_h + (size_t)col8 * W, h[c]);      // one 128 B line per warp store
+                                        float hi, lo;
+                                        split_tf32(z[c], hi, lo);
+                                        const uint32_t a = zaddr[col8 & 7] + (uint32_t)(col8 >> 3) * 1024u;
+                                        sts_f32(a, hi);
+                                        sts_f32(a + lo_delta, lo);
+                                    }
                                 }
                             }
                         }
+                        if (stamp) dst[2] = clock64();
+                        if constexpr (kZeroAcc && !kFirst) tmem_wait_st();
+                        if (l < p.L - 1) {
+                            // publish: smem writes -> async proxy, TMEM reads retired, then one arrive per warp
+                            fence_proxy_async();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&act_ready[mb]);
+                        }
+                        if (stamp) dst[3] = clock64();
                     }
-                    if (stamp) dst[2] = clock64();
-                    if (l < p.L - 1) {
-                        // publish: smem writes -> async proxy, TMEM reads retired, then one arrive per warp
-                        fence_proxy_async();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&act_ready[mb]);
-                    }
-                    if (stamp) dst[3] = clock64();
+                    if constexpr (!kFirst) acc_ph ^= 1;
                 };
                 if (stash_row) {
                     layer_body(std::true_type{}, std::true_type{}, 0);
@@ -600,13 +750,13 @@ __global__ void __launch_bounds__(tc_threads(W), 1) jet_forward_tc_kernel(const 
                         const int pt = col / J, c = col - pt * J;
 #pragma unroll
                         for (int o = 0; o < TDE_MAX_OUT; ++o)
-                            if (o < p.n_out) ybuf[(c * p.n_out + o) * kTcPoints + pt] = y[o] + (c == 0 ? bout_s[o] : 0.0f);
+                            if (o < p.n_out) ybuf[(c * p.n_out + o) * PTS + pt] = y[o] + (c == 0 ? bout_s[o] : 0.0f);
                     }
                 }
                 epi_sync();
                 if (tstamp) p.dbg_buf[43] = clock64();      // output layer computed
-                for (int i = et; i < J * p.n_out * kTcPoints; i += n_epi) {
-                    const int r = i / kTcPoints, pt = i - r * kTcPoints;
+                for (int i = et; i < J * p.n_out * PTS; i += n_epi) {
+                    const int r = i / PTS, pt = i - r * PTS;
                     const int64_t gp = pbase + pt;
                     if (gp < p.B) p.out[(size_t)r * p.ld_out + gp] = ybuf[i];
                 }

@@ -11,8 +11,8 @@
 
 namespace tde {
 
-// single-CTA tensor-core kernels exist where the merged N = 2 x 16 J MMA and a cross-term accumulator set fit
-template <int NF, int SMASK, int W, bool OK = tc_shape_ok(W / 128, kTcPoints * JetSpecT<NF, SMASK>::J)>
+// single-CTA tensor-core kernels exist where the merged N = 2 x PTS J MMA and the accumulator sets the scheme needs fit
+template <int NF, int SMASK, int W, bool OK = tc_shape_ok(W / 128, tc_points(W, JetSpecT<NF, SMASK>::J) * JetSpecT<NF, SMASK>::J)>
 struct TcKernels {
     static void (*fwd())(TcParams) { return jet_forward_tc_kernel<NF, SMASK, W>; }
     static void (*bwd())(TcBwdParams) { return jet_backward_tc_kernel<NF, SMASK, W>; }
@@ -51,8 +51,9 @@ cudaError_t TDE_CAT(launch_backward_, TDE_NF, _, TDE_SMASK)(const JetParams& p, 
 }
 
 cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p, int grid, int smem, cudaStream_t st) {
-    void (*k)(TcParams) = p.W == 256 ? TcKernels<TDE_NF, TDE_SMASK, 256>::fwd() : TcKernels<TDE_NF, TDE_SMASK, 128>::fwd();
-    int threads = tc_threads(p.W), cluster = kTcCluster;
+    void (*k)(TcParams) = p.W == 512 ? TcKernels<TDE_NF, TDE_SMASK, 512>::fwd()
+                          : p.W == 256 ? TcKernels<TDE_NF, TDE_SMASK, 256>::fwd() : TcKernels<TDE_NF, TDE_SMASK, 128>::fwd();
+    int threads = tc_threads(p.W, tc_points(p.W, JetSpecT<TDE_NF, TDE_SMASK>::J)), cluster = kTcCluster;
     if (p.pair) {
         k = PairKernels<TDE_NF, TDE_SMASK>::fwd();
         threads = kPairThreads;
@@ -78,8 +79,9 @@ cudaError_t TDE_CAT(launch_forward_tc_, TDE_NF, _, TDE_SMASK)(const TcParams& p,
 }
 
 cudaError_t TDE_CAT(launch_backward_tc_, TDE_NF, _, TDE_SMASK)(const TcBwdParams& p, int grid, int smem, cudaStream_t st) {
-    void (*k)(TcBwdParams) = p.W == 256 ? TcKernels<TDE_NF, TDE_SMASK, 256>::bwd() : TcKernels<TDE_NF, TDE_SMASK, 128>::bwd();
-    int threads = tc_threads(p.W), cluster = kTcCluster;
+    void (*k)(TcBwdParams) = p.W == 512 ? TcKernels<TDE_NF, TDE_SMASK, 512>::bwd()
+                             : p.W == 256 ? TcKernels<TDE_NF, TDE_SMASK, 256>::bwd() : TcKernels<TDE_NF, TDE_SMASK, 128>::bwd();
+    int threads = tc_threads(p.W, tc_points(p.W, JetSpecT<TDE_NF, TDE_SMASK>::J)), cluster = kTcCluster;
     if (p.pair) {
         k = PairKernels<TDE_NF, TDE_SMASK>::bwd();
         threads = kPairThreads;

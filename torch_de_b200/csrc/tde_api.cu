@@ -148,7 +148,9 @@ struct Geometry {
     int64_t o_w_in, o_b_in, o_wt, o_wn, o_bh, o_wo, o_bo, o_wc, packed_floats;
     // tcgen05 forward (wide layers)
     int use_tc, use_pair, tc_mb, tc_stages, tc_smem, tc_nacc;
+    int tc_pts, tc_ksc;          // points per tensor-core tile (16; 8 for W = 512), k-steps per weight chunk
     int use_tc_bwd, dw_smem;
+    int dw_w, dw_split;          // weight-gradient GEMM: block edge one CTA accumulates (<= 256), halves per dimension (W = 512: 2)
     int64_t o_wct, o_hbar, grid_b1, grid_b2;
     int64_t tc_tiles;
     // per-CTA partial gradient slab
@@ -294,21 +296,24 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     // tcgen05 forward: W in {128, 256}, accumulators of all neuron blocks fit 256 TMEM columns, backward tile is a
     // multiple of the 16-point tensor tile.  TDE_NO_TC=1 forces the FFMA path (A/B measurements, debugging).
     g.use_tc = 0;
+    g.tc_pts = tde::tc_points(g.W, g.J);
     {
-        const int Ntc = tde::kTcPoints * g.J;
+        const int Ntc = g.tc_pts * g.J;
         const int mb = g.W / 128;
+        g.tc_ksc = tde::tc_ksc(g.W, Ntc);
         const bool no_tc = options().no_tc != 0;
         // W = 128: single-CTA kernels, N = 16 J columns per MMA.  W = 256: CTA-pair kernels (cta_group::2), N = 32 J <= 256.
         // TDE_TC_PAIR=1 (W = 256, N = 32 J <= 256): CTA-pair kernels (cta_group::2) instead of the single-CTA ones
         g.use_pair = g.W == 256 && 6 * Ntc <= 512 && options().tc_pair == 1;
-        const bool shape_ok = (g.W == 128 || g.W == 256) && (g.use_pair || tde::tc_shape_ok(mb, Ntc));
-        if (shape_ok && L >= 2 && g.TP % tde::kTcPoints == 0 && !no_tc) {
+        const bool shape_ok = (g.W == 128 || g.W == 256 || g.W == 512) && (g.use_pair || tde::tc_shape_ok(mb, Ntc));
+        // (W <= 256 can pair a tensor-core forward with the FFMA reverse sweep: its tile must then be whole tensor tiles)
+        if (shape_ok && L >= 2 && (g.W > 256 || g.TP % g.tc_pts == 0) && !no_tc) {
             const int64_t atomk = (Ntc / 8) * 1024;
-            const int pts = g.use_pair ? 2 * tde::kTcPoints : tde::kTcPoints;     // points staged per CTA (x, seeds)
+            const int pts = g.use_pair ? 2 * tde::kTcPoints : g.tc_pts;     // points staged per CTA (x, seeds)
             // [planes][weight stages][w_out][x][seeds | y, 4 (padded) outputs per channel][tail: barriers]; the pair kernels keep a 1 KB header
             const int64_t fixed = (g.use_pair ? 1024 : tde::kTcTailBytes) + 2 * (g.W / 32) * atomk +
                                   4 * ((int64_t)g.n_out * g.W + pts * g.d_in + (int64_t)g.J * 4 * pts);
-            const int64_t chunk = g.use_pair ? tde::kPairChunkBytes : (int64_t)mb * 2 * 2 * 2048;
+            const int64_t chunk = g.use_pair ? tde::kPairChunkBytes : (int64_t)g.tc_ksc * 8192;
             for (int st = tde::kTcMaxStages; st >= 2; --st)
                 if (fixed + st * chunk <= kSmemLimit) {
                     if (options().tc_stages > 0) st = std::max(2, std::min(st, options().tc_stages));   // experiments only
@@ -317,13 +322,20 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
                     break;
                 }
         }
-        g.tc_tiles = B > 0 ? (B + tde::kTcPoints - 1) / tde::kTcPoints : 0;
+        // whole 16-point tiles of the weight-gradient GEMM: with 4- or 8-point sweep tiles the tail is padded with tiles of
+        // x = 0 / seeds = 0 (they write finite stash rows and exact-zero Hbar rows, so the GEMM reads nothing uninitialised)
+        const int64_t per16 = std::max(1, 16 / g.tc_pts);
+        g.tc_tiles = B > 0 ? ((B + g.tc_pts - 1) / g.tc_pts + per16 - 1) / per16 * per16 : 0;
     }
+    g.dw_split = g.W > 256 ? 2 : 1;
+    g.dw_w = g.W / g.dw_split;
+    g.dw_smem = 1024 + (tde::kDwStages * 4 + tde::dw_raw_stages(g.J) * 2) * g.dw_w * 32;
+    // W = 512: the forward and the reverse sweep switch together (the FFMA sweep is not paired with the 8-point-tile forward)
+    if (g.W > 256 && (g.J > 6 || g.dw_smem > kSmemLimit || options().no_tc_bwd)) g.use_tc = 0;
     o = align_up(o, 64);
     g.o_wc = o;   if (g.use_tc) o += (int64_t)(L - 1) * 2 * WW;
     g.use_tc_bwd = 0;
     {
-        g.dw_smem = 1024 + (tde::kDwStages * 4 + tde::dw_raw_stages(g.J) * 2) * g.W * 32;
         if (g.use_tc && g.J <= 6 && g.dw_smem <= kSmemLimit && !options().no_tc_bwd) {
             g.use_tc_bwd = 1;
             g.rsplit = 1;      // the FFMA dW phase (and its column split) is not used on this path
@@ -335,7 +347,8 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     int64_t q = 0;
     q = align_up((int64_t)g.W * g.d_in, 4);
     g.g_b_in = q;   q = align_up(q + g.W, 4);
-    g.g_hidden = q; q += (int64_t)(L - 1) * g.rsplit * WW;
+    // hidden dW: [layer][n][k]; the W = 512 tensor path keeps one 256 x 256 quadrant per CTA
+    g.g_hidden = q; q += (int64_t)(L - 1) * g.rsplit * (g.use_tc_bwd ? (int64_t)g.dw_w * g.dw_w : WW);
     g.g_bh = q;     q += (int64_t)(L - 1) * g.W;
     g.g_wo = q;     q = align_up(q + (int64_t)g.n_out * g.W, 4);
     g.g_bo = q;     q = align_up(q + g.n_out, 4);
@@ -345,7 +358,7 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         // the tcgen05 reverse sweep has several threads per neuron (one per group of 8 points: 2 for W = 128, 4 for the CTA
         // pair): each adds into its own copy of (w_in | b_in) and (b_hidden | w_out); the reduction sums the copies in a
         // fixed order
-        g.n_copies = g.use_pair ? 4 : 2;
+        g.n_copies = g.use_pair ? 4 : g.tc_pts / tde::tc_visit_points(g.W, g.tc_pts);
         const int64_t small_end = q;
         const int64_t dup_size = align_up(g.g_hidden + (small_end - g.g_bh), 4);
         for (int k = 1; k < g.n_copies; ++k) {
@@ -362,7 +375,7 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
     if (g.use_tc) {
         const int cl = g.use_pair ? tde::kPairCluster : tde::kTcCluster;
         const int64_t padded = (g.tc_tiles + cl - 1) / cl * cl;
-        g.stash_layer_stride = std::max<int64_t>(g.stash_layer_stride, padded * tde::kTcPoints * (int64_t)g.J * g.W);
+        g.stash_layer_stride = std::max<int64_t>(g.stash_layer_stride, padded * (g.use_pair ? tde::kTcPoints : g.tc_pts) * (int64_t)g.J * g.W);
     }
     g.stash_floats = (int64_t)L * g.stash_layer_stride;
     g.stash_total_floats = g.stash_floats;
@@ -375,7 +388,11 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         const int cl = g.use_pair ? tde::kPairCluster : tde::kTcCluster;
         const int64_t groups = (g.tc_tiles + cl - 1) / cl;
         g.grid_b1 = cl * std::max<int64_t>(1, std::min<int64_t>(tc_cluster_slots(g.disp, g.use_pair != 0, g.tc_smem), groups));
-        g.grid_b2 = std::max<int64_t>(1, std::min<int64_t>(sm_count(), g.tc_tiles));
+        // weight-gradient GEMM walks 16-point tiles (two 8-point tiles of the W = 512 sweep); one CTA per SM, a multiple of the
+        // quadrant count, never more tile groups than tiles
+        const int64_t dw_tiles = g.tc_tiles * g.tc_pts / 16 + ((g.tc_tiles * g.tc_pts) % 16 ? 1 : 0);
+        const int nq = g.dw_split * g.dw_split;
+        g.grid_b2 = nq * std::max<int64_t>(1, std::min<int64_t>(sm_count() / nq, dw_tiles));
     }
 
     int64_t np = 0;
@@ -444,11 +461,11 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackArgs a, float* _
 
 // tcgen05 operand image of the hidden weights: per layer, per 8-k chunk: [hi|lo][neuron block][k group of 4][16 row
 // groups][8 rows][4 k] -- exactly the shared-memory layout of the K-major SWIZZLE_NONE UMMA A operand, split 3xTF32.
-__global__ void pack_tc_weights_kernel(const __grid_constant__ PackArgs a, float* __restrict__ wc, int MB, int transpose) {
+__global__ void pack_tc_weights_kernel(const __grid_constant__ PackArgs a, float* __restrict__ wc, int MB, int KSC, int transpose) {
     const int W = a.W;
     const int64_t per_layer = 2LL * W * W;
     const int64_t total = (int64_t)(a.L - 1) * per_layer;
-    const int chunk = MB * 2 * 2 * 512;   // floats per chunk
+    const int chunk = KSC * 2048;         // floats per chunk: one neuron block, KSC k-steps of [hi 1024 | lo 1024]
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int l = (int)(i / per_layer) + 1;
         int64_t r = i % per_layer;
@@ -459,12 +476,13 @@ __global__ void pack_tc_weights_kernel(const __grid_constant__ PackArgs a, float
             ks = ci;
             mb = 0;
             hl = c / 1024;      c %= 1024;
-        } else {                // MB == 2: chunks follow the issue order of tc_issue_layer: quarter (mb, k half), two k-steps each
-            const int per_q = W / 32;          // chunks per quarter
+        } else {                // MB >= 2: chunks follow the issue order of tc_issue_layer(_wide): units (k range of 128 inputs kq,
+                                // neuron block mb), kq-major, each 16 k-steps = 16 / KSC chunks
+            const int per_q = 16 / KSC;        // chunks per unit
             const int q = ci / per_q, cc = ci % per_q;
-            mb = q & 1;
+            mb = q % MB;
             const int s2 = c / 2048; c %= 2048;
-            ks = (q >> 1) * (W / 16) + cc * 2 + s2;
+            ks = (q / MB) * 16 + cc * KSC + s2;
             hl = c / 1024;      c %= 1024;
         }
         kg = c / 512;           c %= 512;
@@ -493,12 +511,12 @@ int launch_pack(const TdeNet* net, const Geometry& g, float* ws, bool want_wt, b
     ++g_launches;
     TDE_CUDA(cudaGetLastError());
     if (want_wt && g.use_tc) {
-        pack_tc_weights_kernel<<<148 * 4, threads, 0, st>>>(a, ws + g.o_wc, g.tc_mb, 0);
+        pack_tc_weights_kernel<<<148 * 4, threads, 0, st>>>(a, ws + g.o_wc, g.tc_mb, g.tc_ksc, 0);
         ++g_launches;
         TDE_CUDA(cudaGetLastError());
     }
     if (want_wn && g.use_tc_bwd) {
-        pack_tc_weights_kernel<<<148 * 4, threads, 0, st>>>(a, ws + g.o_wct, g.tc_mb, 1);
+        pack_tc_weights_kernel<<<148 * 4, threads, 0, st>>>(a, ws + g.o_wct, g.tc_mb, g.tc_ksc, 1);
         ++g_launches;
         TDE_CUDA(cudaGetLastError());
     }
@@ -527,6 +545,8 @@ struct ReduceArgs {
     int64_t g_b_in, g_hidden, g_bh, g_wo, g_bo;
     int n_copies;                // copies of the small sections (tcgen05 reverse sweep: one per thread of a neuron)
     int64_t dup_lo[4], dup_hi[4];
+    int dw_w, dw_split;          // tensor-core weight-gradient GEMM: hidden dW kept as dw_split^2 quadrants of dw_w x dw_w, slab c holds
+                                 // quadrant c % dw_split^2 (dw_split = 1: the whole matrix in every slab)
     float scale;
 };
 
@@ -537,7 +557,7 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
     // decode flat index -> (layer, weight|bias, row, col)
     int64_t r = i;
     int64_t src = -1;
-    int splits = 1;
+    int splits = 1, slab0 = 0, slab_step = 1;
     const int L = a.n_layers - 1;
     const int64_t WW = (int64_t)a.W * a.W;
     // layer 0
@@ -555,7 +575,13 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
             const int64_t rr = r % per;
             if (rr < (int64_t)a.width * a.width) {
                 const int n = (int)(rr / a.width), k = (int)(rr % a.width);
-                src = a.g_hidden + (int64_t)l * a.rsplit * WW + (int64_t)n * a.W + k;
+                if (a.dw_split > 1) {
+                    slab0 = (n / a.dw_w) * a.dw_split + (k / a.dw_w);
+                    slab_step = a.dw_split * a.dw_split;
+                    src = a.g_hidden + (int64_t)l * a.dw_w * a.dw_w + (int64_t)(n % a.dw_w) * a.dw_w + (k % a.dw_w);
+                } else {
+                    src = a.g_hidden + (int64_t)l * a.rsplit * WW + (int64_t)n * a.W + k;
+                }
                 splits = a.rsplit;
             } else {
                 src = a.g_bh + (int64_t)l * a.W + (rr - (int64_t)a.width * a.width);
@@ -571,7 +597,7 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
         }
     }
     float s = 0.0f;
-    const int n_slabs = splits > 1 || src >= a.g_hidden && src < a.g_bh ? a.n_active_hidden : a.n_active;
+    const int n_slabs = splits > 1 || src >= a.g_hidden && src < a.g_bh ? a.n_active_hidden / slab_step : a.n_active;
     const int which = src < a.g_hidden ? 1 : (src >= a.g_bh && src < a.g_bo ? 2 : 0);
     if (splits == 1 && !(which && a.n_copies > 1)) {
         // common case (hidden weights on the tensor path): one value per slab.  Eight loads are in flight at a time; the
@@ -580,11 +606,11 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
         for (; c + 8 <= n_slabs; c += 8) {
             float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcs(gpart + (int64_t)(c + u) * a.gp_stride + src);
+            for (int u = 0; u < 8; ++u) v[u] = __ldcs(gpart + (int64_t)(slab0 + (c + u) * slab_step) * a.gp_stride + src);
 #pragma unroll
             for (int u = 0; u < 8; ++u) s += v[u];
         }
-        for (; c < n_slabs; ++c) s += __ldcs(gpart + (int64_t)c * a.gp_stride + src);
+        for (; c < n_slabs; ++c) s += __ldcs(gpart + (int64_t)(slab0 + c * slab_step) * a.gp_stride + src);
     } else {
         for (int c = 0; c < n_slabs; ++c) {
             const float* slab = gpart + (int64_t)c * a.gp_stride + src;
@@ -913,16 +939,12 @@ int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, i
     return 0;
 }
 
-int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points, const float* stash,
-                     const float* seeds, int64_t ld_seeds, float grad_scale, float* flat_grad, void* workspace,
-                     void* stream) {
-    Geometry g;
-    if (int rc = make_geometry(net, spec, n_points, &g)) return rc;
-    if (n_points == 0) return 0;
-    if (!x || !stash || !seeds || !flat_grad || !workspace) return fail("null x/stash/seeds/flat_grad/workspace");
-    if (ld_seeds < n_points) return fail("ld_seeds %lld < n_points %lld", (long long)ld_seeds, (long long)n_points);
-    cudaStream_t st = (cudaStream_t)stream;
-    float* ws = (float*)workspace;
+// Reverse sweep + weight gradient + second-stage reduction over the points the buffers start at.  `g` is the geometry of the
+// launch (tile counts, grids, workspace offsets); its stash_layer_stride is the stride of the stash the pointers index into
+// (a range call points into the stash of a larger forward).
+static int backward_core(const TdeNet* net, const TdeJetSpec* spec, const Geometry& g, const float* x, int64_t n_points,
+                         const float* stash, const float* seeds, int64_t ld_seeds, float grad_scale, float* flat_grad, float* ws,
+                         cudaStream_t st) {
     if (int rc = launch_pack(net, g, ws, false, true, st)) return rc;
     int n_active = g.n_ctas, n_active_hidden = g.n_ctas;
     if (g.use_tc_bwd) {
@@ -940,7 +962,8 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
         t.gp_off_b_in = g.g_b_in; t.gp_off_b_hidden = g.g_bh; t.gp_off_w_out = g.g_wo; t.gp_off_b_out = g.g_bo;
         for (int k = 0; k < 4; ++k) { t.gp_dup_lo[k] = g.g_dup_lo[k]; t.gp_dup_hi[k] = g.g_dup_hi[k]; }
         tde::TcDwParams d{};
-        d.n_tiles = g.tc_tiles; d.L = g.L; d.W = g.W; d.MB = g.tc_mb; d.J = g.J;
+        d.n_tiles = (g.tc_tiles * g.tc_pts + 15) / 16;     // the weight-gradient GEMM walks 16-point tiles whatever the sweep's tile
+        d.L = g.L; d.W = g.dw_w; d.MB = g.dw_w / 128; d.J = g.J; d.Wr = g.W; d.n_split = g.dw_split;
         d.hbar = t.hbar; d.stash = stash; d.act = g.act; d.fourier_half = g.fourier_half;
         d.stash_layer_stride = t.stash_layer_stride; d.tiles_per_bw_tile = t.tiles_per_bw_tile;
         d.gpart = t.gpart; d.gp_stride = g.gp_stride; d.gp_off_hidden = g.g_hidden;
@@ -991,12 +1014,50 @@ int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, 
     r.rsplit = g.rsplit; r.n_active = n_active; r.n_active_hidden = n_active_hidden; r.n_params = g.n_params; r.gp_stride = g.gp_stride;
     r.g_b_in = g.g_b_in; r.g_hidden = g.g_hidden; r.g_bh = g.g_bh; r.g_wo = g.g_wo; r.g_bo = g.g_bo;
     r.n_copies = g.n_copies;
+    r.dw_w = g.dw_w; r.dw_split = g.use_tc_bwd ? g.dw_split : 1;
     for (int k = 0; k < 4; ++k) { r.dup_lo[k] = g.g_dup_lo[k]; r.dup_hi[k] = g.g_dup_hi[k]; }
     r.scale = grad_scale;
     const int threads = 256;
     reduce_grads_kernel<<<(int)((g.n_params + threads - 1) / threads), threads, 0, st>>>(r, ws + g.o_gpart, flat_grad);
     TDE_CUDA(cudaGetLastError());
     return 0;
+}
+
+int tde_jet_backward(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points, const float* stash,
+                     const float* seeds, int64_t ld_seeds, float grad_scale, float* flat_grad, void* workspace,
+                     void* stream) {
+    Geometry g;
+    if (int rc = make_geometry(net, spec, n_points, &g)) return rc;
+    if (n_points == 0) return 0;
+    if (!x || !stash || !seeds || !flat_grad || !workspace) return fail("null x/stash/seeds/flat_grad/workspace");
+    if (ld_seeds < n_points) return fail("ld_seeds %lld < n_points %lld", (long long)ld_seeds, (long long)n_points);
+    return backward_core(net, spec, g, x, n_points, stash, seeds, ld_seeds, grad_scale, flat_grad, (float*)workspace, (cudaStream_t)stream);
+}
+
+static int64_t gcd64(int64_t a, int64_t b) { return b == 0 ? a : gcd64(b, a % b); }
+
+int tde_jet_backward_range(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points, const float* stash,
+                           const float* seeds, int64_t ld_seeds, int64_t p_lo, int64_t p_hi, float grad_scale,
+                           float* flat_grad, void* workspace, void* stream) {
+    Geometry g;
+    if (int rc = make_geometry(net, spec, n_points, &g)) return rc;
+    if (p_lo < 0 || p_hi > n_points || p_lo > p_hi) return fail("range [%lld, %lld) outside [0, %lld)", (long long)p_lo, (long long)p_hi, (long long)n_points);
+    if (p_lo == p_hi) return 0;
+    if (!x || !stash || !seeds || !flat_grad || !workspace) return fail("null x/stash/seeds/flat_grad/workspace");
+    if (ld_seeds < n_points) return fail("ld_seeds %lld < n_points %lld", (long long)ld_seeds, (long long)n_points);
+    // whole tiles of every kernel on the path: the FFMA tile (g.TP points) and the cluster's pair of 16-point tiles of the
+    // tensor-core kernels (the sub-range's own padding tile must stay inside the padded extent of the full stash / Hbar).
+    // Every layer of the stash is [tile][W x (tile points x J)] in both layouts, so a tile-aligned point offset p is the same
+    // float offset p * J * W inside each layer.
+    const int64_t align = (int64_t)g.TP / gcd64(g.TP, 32) * 32;
+    const int64_t lo = p_lo / align * align;
+    Geometry gs;
+    if (int rc = make_geometry(net, spec, p_hi - lo, &gs)) return rc;
+    if (gs.use_tc != g.use_tc || gs.use_tc_bwd != g.use_tc_bwd || gs.TP != g.TP || gs.workspace_floats > g.workspace_floats)
+        return fail("range call plans a different kernel path than the forward that wrote the stash");
+    gs.stash_layer_stride = g.stash_layer_stride;
+    return backward_core(net, spec, gs, x + lo * g.d_in, p_hi - lo, stash + lo * (int64_t)g.J * g.W, seeds + lo, ld_seeds, grad_scale,
+                         flat_grad, (float*)workspace, (cudaStream_t)stream);
 }
 
 int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,

@@ -68,6 +68,7 @@ class JetRunner:
         self._net.n_layers = len(self.lins)
         self._plans: Dict[int, _lib.TdePlan] = {}
         self._workspace: Optional[torch.Tensor] = None
+        self._last_forward = None
         self._chunk_stash: Optional[torch.Tensor] = None
         self.chunking: Dict[tuple, int] = {}
 
@@ -150,9 +151,12 @@ class JetRunner:
         return x, out, stash
 
     def backward(self, x: torch.Tensor, tensors: Sequence[torch.Tensor], stash: torch.Tensor, seeds: torch.Tensor,
-                 flat_grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0, seeds_ld: int = 0) -> torch.Tensor:
+                 flat_grad: Optional[torch.Tensor] = None, grad_scale: float = 1.0, seeds_ld: int = 0,
+                 point_range: Optional[tuple] = None) -> torch.Tensor:
         """seeds: [rows, B] block; with seeds_ld > 0 it is a column slice of a wider contiguous block whose row
-        pitch is seeds_ld (recompute mode passes views, no copy)."""
+        pitch is seeds_ld (recompute mode passes views, no copy).
+        point_range = (lo, hi): the seeds are zero outside these points, sweep only the tiles that hold them
+        (tde_jet_backward_range; the fused GradNorm's per-row gradients)."""
         B = x.shape[0]
         if flat_grad is None:
             flat_grad = torch.zeros(self.n_params, dtype=torch.float32, device=x.device)
@@ -167,9 +171,14 @@ class JetRunner:
         self._bind(tensors)
         ws = self._ws(plan.workspace_bytes, x.device)
         with _lib.on_device(x.device):
-            rc = _lib.lib().tde_jet_backward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, stash.data_ptr(),
-                                             seeds.data_ptr(), seeds_ld, grad_scale, flat_grad.data_ptr(), ws.data_ptr(),
-                                             self._stream(x.device))
+            if point_range is None:
+                rc = _lib.lib().tde_jet_backward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, stash.data_ptr(),
+                                                 seeds.data_ptr(), seeds_ld, grad_scale, flat_grad.data_ptr(), ws.data_ptr(),
+                                                 self._stream(x.device))
+            else:
+                rc = _lib.lib().tde_jet_backward_range(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, stash.data_ptr(),
+                                                       seeds.data_ptr(), seeds_ld, int(point_range[0]), int(point_range[1]),
+                                                       grad_scale, flat_grad.data_ptr(), ws.data_ptr(), self._stream(x.device))
         _lib.check(rc, "tde_jet_backward")
         return flat_grad
 
@@ -220,6 +229,9 @@ class _JetFunction(torch.autograd.Function):
         ctx.stash = stash
         ctx.need = need
         ctx.save_for_backward(xc, *params)
+        # what a caller needs to run further reverse sweeps on this forward without autograd (fused GradNorm): picked up by
+        # Jet_engine._jets right after apply()
+        runner._last_forward = (xc, stash, params) if stash is not None else None
         return out
 
     @staticmethod
@@ -240,6 +252,22 @@ class _JetFunction(torch.autograd.Function):
                 runner.backward(xc, params, stash, grad_out[:, lo:hi], flat_grad=flat, seeds_ld=B)
                 del stash
         return (None, None, *runner.split_flat(flat))
+
+
+class JetForwardRecord:
+    """Handle on one stash-keeping forward: lets `grad_balance.GradNorm` run range-restricted reverse sweeps on it."""
+    __slots__ = ('runner', 'net', 'x', 'stash', 'params')
+
+    def __init__(self, runner, net, x, stash, params):
+        self.runner, self.net, self.x, self.stash, self.params = runner, net, x, stash, params
+
+    def gradient(self, seeds: torch.Tensor, point_range=None, flat_grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """flat parameter gradient (net.parameters() order of the Linear layers) of sum(seeds * block)."""
+        if point_range is not None:
+            lo, hi = point_range
+            if hi <= lo:
+                return flat_grad if flat_grad is not None else torch.zeros(self.runner.n_params, dtype=torch.float32, device=self.x.device)
+        return self.runner.backward(self.x, self.params, self.stash, seeds, flat_grad=flat_grad, point_range=point_range)
 
 
 class JetOutput(dict):
@@ -274,7 +302,12 @@ class Jet_engine(_EngineBase):
 
     # -- helpers -----------------------------------------------------------------------------
     def _jets(self, runner: JetRunner, x: torch.Tensor) -> torch.Tensor:
-        return _JetFunction.apply(x, runner, *runner.effective_tensors())
+        runner._last_forward = None
+        block = _JetFunction.apply(x, runner, *runner.effective_tensors())
+        if runner._last_forward is not None:
+            block._tde_forward = JetForwardRecord(runner, self.net, *runner._last_forward)
+            runner._last_forward = None
+        return block
 
     def _named(self, runner: JetRunner, block: torch.Tensor, names, lo=None, hi=None) -> Dict[str, torch.Tensor]:
         if lo is None:

@@ -38,7 +38,14 @@ class Sym:
         if isinstance(v, numbers.Real):
             return Sym('const', imm=float(v))
         if isinstance(v, torch.Tensor) and v.numel() == 1:
-            return Sym('const', imm=float(v))
+            # A tensor scalar (an annealed Re, a PDE coefficient of an inverse problem ...) is NOT baked into the program: a
+            # learnable one needs autograd (torch path), any other one is re-read from the tensor at every launch through an
+            # aux row, so a value changed in place between steps is seen.
+            if v.requires_grad:
+                raise TraceError('a learnable scalar in a residual needs the torch path (its gradient)')
+            if _TRACE is None:
+                raise TraceError('tensor scalar outside a trace')
+            return Sym('aux', imm=_TRACE.scalar_slot(v))
         raise TraceError(f'cannot mix {type(v).__name__} into a traced residual')
 
     def _bin(self, other, op, swap=False):
@@ -94,6 +101,22 @@ class Sym:
                 out.add(n.imm)
             stack.extend(n.args)
         return out
+
+
+class _TraceContext:
+    """Tensor scalars met while tracing one group: each becomes the aux leaf '__s<k>' that is re-read every launch."""
+    def __init__(self):
+        self.scalars: List[torch.Tensor] = []
+
+    def scalar_slot(self, t: torch.Tensor) -> str:
+        for k, u in enumerate(self.scalars):
+            if u is t:
+                return f'__s{k}'
+        self.scalars.append(t)
+        return f'__s{len(self.scalars) - 1}'
+
+
+_TRACE: Optional[_TraceContext] = None
 
 
 class _GroupProxy:
@@ -164,6 +187,8 @@ class GroupProgram:
             prog.ops[k].op, prog.ops[k].dst, prog.ops[k].a, prog.ops[k].b, prog.ops[k].imm = op, dst, a, b, imm
         self.prog = prog
         self.weight_aux: List[Optional[int]] = [None] * len(res_syms)
+        self.scalars: List[torch.Tensor] = []          # tensor scalars behind the '__s<k>' aux rows
+        self.signature = tuple(s.key for s in res_syms)   # structure + baked Python constants of the traced rows
 
     def _aux(self, name: str) -> int:
         if name not in self.aux_names:
@@ -180,19 +205,38 @@ class GroupProgram:
 
 def trace_group(group, rows: List[dict], stream_row: Dict[str, int], n_stream_rows: int) -> GroupProgram:
     """rows: Loss_handler records of ONE group (non-custom). Raises TraceError if any row cannot be fused."""
+    syms, ctx = trace_rows(group, rows, stream_row)
+    prog = GroupProgram(getattr(group, 'name', None), list(range(len(rows))), syms, stream_row, n_stream_rows)
+    prog.scalars = ctx.scalars
+    return prog
+
+
+def trace_rows(group, rows: List[dict], stream_row: Dict[str, int]):
+    """Symbolic evaluation of the rows' own callables (pure Python, no tensor work): the Sym of every row + the trace context."""
+    global _TRACE
     gp = _GroupProxy(group)
     outs = {name: Sym('load', imm=name) for name in stream_row}
-    syms = []
-    for spec in rows:
-        r = spec['evaluation'](gp, outs)
-        syms.append(Sym.lift(r))
-    return GroupProgram(getattr(group, 'name', None), list(range(len(rows))), syms, stream_row, n_stream_rows)
+    prev, _TRACE = _TRACE, _TraceContext()
+    try:
+        syms = [Sym.lift(spec['evaluation'](gp, outs)) for spec in rows]
+        return syms, _TRACE
+    finally:
+        _TRACE = prev
+
+
+def signature_of(group, rows: List[dict], stream_row: Dict[str, int]) -> tuple:
+    """Signature of what the rows trace to NOW: differs from a cached program's when a Python number captured by a residual
+    closure (or a group's unbatchable) changed since that program was compiled."""
+    syms, _ = trace_rows(group, rows, stream_row)
+    return tuple(s.key for s in syms)
 
 
 def eval_weight(spec: dict, group, out_names) -> object:
     """Per-point weight of a row, evaluated with torch on the real inputs (weights are constants of the step)."""
     w = spec.get('weighting_spec', 1)
     if not callable(w):
+        if isinstance(w, torch.Tensor) and w.numel() > 1:      # a fixed per-point weight tensor
+            return w.detach().to(torch.float32)
         return float(w)
     guard = {k: _Guard() for k in out_names}
     with torch.no_grad():
@@ -213,13 +257,14 @@ class _FusedRows(torch.autograd.Function):
         lib = _lib.lib()
         stream = torch.cuda.current_stream(block.device).cuda_stream
         off = 0
-        for gp, aux, lo, n in launches:
-            if n > 0:
-                rc = lib.tde_residual_loss(C.byref(gp.prog), block.data_ptr(), B, gp.n_stream_rows,
-                                           aux.data_ptr() if aux is not None else None, n, lo, n, 1.0 / n, None,
-                                           rows.data_ptr() + 4 * off, None, None, stream)
-                _lib.check(rc, 'tde_residual_loss')
-            off += gp.prog.n_rows
+        with _lib.on_device(block.device):
+            for gp, aux, lo, n in launches:
+                if n > 0:
+                    rc = lib.tde_residual_loss(C.byref(gp.prog), block.data_ptr(), B, gp.n_stream_rows,
+                                               aux.data_ptr() if aux is not None else None, n, lo, n, 1.0 / n, None,
+                                               rows.data_ptr() + 4 * off, None, None, stream)
+                    _lib.check(rc, 'tde_residual_loss')
+                off += gp.prog.n_rows
         ctx.launches = launches
         ctx.save_for_backward(block)
         return rows
@@ -234,13 +279,14 @@ class _FusedRows(torch.autograd.Function):
         lib = _lib.lib()
         stream = torch.cuda.current_stream(block.device).cuda_stream
         off = 0
-        for gp, aux, lo, n in ctx.launches:
-            if n > 0:
-                rc = lib.tde_residual_loss(C.byref(gp.prog), block.data_ptr(), B, gp.n_stream_rows,
-                                           aux.data_ptr() if aux is not None else None, n, lo, n, 1.0 / n,
-                                           grad_rows.data_ptr() + 4 * off, None, seeds.data_ptr(), None, stream)
-                _lib.check(rc, 'tde_residual_loss')
-            off += gp.prog.n_rows
+        with _lib.on_device(block.device):
+            for gp, aux, lo, n in ctx.launches:
+                if n > 0:
+                    rc = lib.tde_residual_loss(C.byref(gp.prog), block.data_ptr(), B, gp.n_stream_rows,
+                                               aux.data_ptr() if aux is not None else None, n, lo, n, 1.0 / n,
+                                               grad_rows.data_ptr() + 4 * off, None, seeds.data_ptr(), None, stream)
+                    _lib.check(rc, 'tde_residual_loss')
+                off += gp.prog.n_rows
         return seeds, None
 
 

@@ -21,6 +21,14 @@ class GroupedLosses(dict):
         return list(self.keys())
 
 
+class RowStack(Tensor):
+    """The stacked row losses.  Iterating it (`*loss.individual_losses()`) yields the original row tensors, which remember the
+    stream block and point range they were computed from (grad_balance.GradNorm's fused path); everything else is a Tensor."""
+    def __iter__(self):
+        rows = getattr(self, '_rows', None)
+        return iter(rows) if rows is not None else super().__iter__()
+
+
 class Loss:
     def __init__(self, rows: List[dict], aggregation_method: str = 'mean', power: Union[int, None] = 2):
         self.losses = rows
@@ -56,6 +64,8 @@ class Loss:
                         row['point_error'] = self.error_func(row['residual'])
                     row['weighted_error'] = row['weighting'] * row['point_error']
                     row['aggregated_loss'] = self._agg(row['weighted_error'])
+                if row.get('_src') is not None:
+                    row['aggregated_loss']._tde_row = row['_src']      # (stream block, point range of the row's group)
             self._done = True
         return [row['aggregated_loss'] for row in self.losses]
 
@@ -63,7 +73,10 @@ class Loss:
         return sum(self.aggregated_loss())
 
     def individual_losses(self) -> Tensor:
-        return torch.stack(list(self.aggregated_loss()))
+        rows = list(self.aggregated_loss())
+        stacked = torch.stack(rows).as_subclass(RowStack)
+        stacked._rows = rows           # `*loss.individual_losses()` (Stokes_Cylinder.py:108) hands GradNorm the row tensors themselves
+        return stacked
 
     def grouped_losses(self, groupby: str) -> GroupedLosses:
         if groupby not in ('loss_type', 'group', 'variable'):
@@ -94,9 +107,13 @@ class Loss:
 
 
 class Loss_handler:
-    def __init__(self, dataset=None, fused: bool = True) -> None:
+    def __init__(self, dataset=None, fused: bool = True, revalidate: bool = True) -> None:
         self.rows: List[dict] = []
         self.fused = fused                 # use tde_residual_loss when the engine output allows it
+        # Re-trace the rows symbolically at every call (pure Python, no tensor work) and recompile a group whose trace
+        # changed: a Python number captured by a residual closure (an annealed viscosity ...) is a constant of the compiled
+        # program.  Tensor scalars never need this (they are re-read on the device); `revalidate=False` skips the check.
+        self.revalidate = revalidate
         self.fusion_report: Dict[str, str] = {}   # group -> 'fused' | reason it stayed on the torch path
         self._programs: Dict[tuple, object] = {}
         self.update_dataset(dataset)
@@ -124,16 +141,24 @@ class Loss_handler:
         if (use_fused and power == 2 and aggregation_method == 'mean'
                 and getattr(batched_output, 'block', None) is not None and batched_output.block.is_cuda):
             fused_groups = self._fused_rows(batched_input, batched_output)
+        block = getattr(batched_output, 'block', None)
+        ranges = getattr(batched_output, 'ranges', None) or {}
+        n_all = block.shape[1] if block is not None else 0
         rows = []
         for spec in self.rows:
+            src = None if block is None else (block, (0, n_all) if spec['custom'] else ranges.get(spec['group']))
+            if src is not None and src[1] is None:
+                src = None
             if not spec['custom'] and spec['group'] in fused_groups:
                 row = dict(spec)
+                row['_src'] = src
                 row['residual'] = None
                 row['weighting'] = None
                 row['aggregated_loss'] = fused_groups[spec['group']].pop(0)
                 rows.append(row)
                 continue
             row = dict(spec)
+            row['_src'] = src
             if spec['custom']:
                 row['residual'] = spec['evaluation'](batched_input, batched_output)
                 row['weighting'] = 1.
@@ -163,6 +188,8 @@ class Loss_handler:
             gp = self._programs.get(key)
             try:
                 weights = [FL.eval_weight(sp, group, names) for sp in specs]
+                if gp and self.revalidate and FL.signature_of(group, specs, out.stream_row) != gp.signature:
+                    gp = None      # a Python constant behind a residual closure changed: compile the rows again
                 if gp is None:
                     gp = FL.trace_group(group, specs, out.stream_row, n_stream_rows)
                     for i, w in enumerate(weights):
@@ -183,7 +210,9 @@ class Loss_handler:
                 for a in gp.aux_names:
                     if a.startswith('__w'):
                         w = weights[int(a[3:])]
-                        cols.append(w if isinstance(w, torch.Tensor) else torch.full((n,), float(w), device=out.block.device))
+                        cols.append(w.to(out.block.device) if isinstance(w, torch.Tensor) else torch.full((n,), float(w), device=out.block.device))
+                    elif a.startswith('__s'):       # tensor scalar of a residual: re-read every launch, no host sync
+                        cols.append(gp.scalars[int(a[3:])].detach().to(device=out.block.device, dtype=torch.float32).reshape(1).expand(n))
                     else:
                         cols.append(group.batchables[a].to(torch.float32))
                 aux = torch.stack(cols).contiguous()
