@@ -140,17 +140,30 @@ int tde_jet_backward_range(const TdeNet* net, const TdeJetSpec* spec, const floa
 #define TDE_OP_SIN 9
 #define TDE_OP_COS 10
 #define TDE_OP_DIV 11
+#define TDE_OP_GRID2D 12 /* dst = bilinear lookup of grids[(int)imm] at (x = reg a, y = reg b): the signed-distance /
+                            point-weight field of utils/GridInterpolator.py:50-83, evaluated inside the loss kernel.
+                            Constant w.r.t. the streams (its arguments are input coordinates): no adjoint. */
 #define TDE_MAX_REGS 64
 #define TDE_MAX_OPS 128
 #define TDE_MAX_ROWS 8
+#define TDE_MAX_GRIDS 2
+
+/* a regular 2-D grid on the device: gx[nx], gy[ny] ascending, values[nx][ny] */
+typedef struct TdeGrid2D {
+    const float* gx;
+    const float* gy;
+    const float* values;
+    int32_t nx, ny;
+} TdeGrid2D;
 
 typedef struct TdeOp {
     int32_t op, dst, a, b;
     float imm;
 } TdeOp;
 
-/* One loss-table group: `n_rows` residuals over the same points; row r reads register res_reg[r],
- * weight is aux row w_aux[r] (or the constant w_const[r] if w_aux[r] < 0); loss_r = coef[r]*mean(w*|res|^2). */
+/* One loss-table group: `n_rows` residuals over the same points; row r reads register res_reg[r]; its per-point weight is
+ * register w_reg[r] (a weighting function traced into the program, e.g. the SDF lookup), else aux row w_aux[r], else the
+ * constant w_const[r]; loss_r = coef[r]*mean(w*|res|^2). */
 typedef struct TdeLossProgram {
     int32_t n_ops;
     int32_t n_rows;
@@ -159,6 +172,10 @@ typedef struct TdeLossProgram {
     int32_t w_aux[TDE_MAX_ROWS];
     float w_const[TDE_MAX_ROWS];
     float coef[TDE_MAX_ROWS];
+    int32_t w_reg[TDE_MAX_ROWS];      /* -1: no traced weight */
+    int32_t n_grids;
+    int32_t reserved;
+    TdeGrid2D grids[TDE_MAX_GRIDS];
 } TdeLossProgram;
 
 /*
@@ -168,11 +185,18 @@ typedef struct TdeLossProgram {
  *   seeds[(row)*ld + p] = sum_r coef_r * inv_count * d(w*res_r^2)/d(stream)   (overwrites the [p0,p0+n) slice of
  *                         every stream row; rows never loaded get zeros); coef_r = prog.coef[r] * coef_dev[r]
  *                         (coef_dev: optional DEVICE array = d total / d row, so no host sync is needed)
- *   point_res[n_rows][n]: per-point residuals (what utils/sampling.py:R3_sampler consumes).
+ *   point_res[n_rows][n]: per-point residuals (what utils/sampling.py:R3_sampler consumes);
+ *   point_w[n_rows][n]   (tde_residual_loss_points only): the per-point weights the rows were reduced with.
  */
 int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
                       const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
                       const float* coef_dev, float* row_sums, float* seeds, float* point_res, void* stream);
+
+/* Same kernel, forward only, emitting what Loss.point_error() / weighted_point_error() and R3_sampler need: the per-point
+ * residuals and weights of every row (either may be NULL). */
+int tde_residual_loss_points(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
+                             const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float* point_res, float* point_w,
+                             void* stream);
 
 /* Adam with torch.optim.Adam's arithmetic (bias-corrected, eps outside sqrt of v_hat; hyper-parameters are doubles rounded to
  * float once, like torch's python scalars), one launch.  `step` counts from 1. */

@@ -12,7 +12,8 @@ ACT_NONE, ACT_TANH, ACT_SIN = 0, 1, 2
 ACT_FOURIER = 0x100
 MAX_LAYERS, MAX_IN, MAX_OUT, MAX_FIRST, MAX_SECOND = 24, 8, 4, 3, 6
 MAX_REGS, MAX_OPS, MAX_ROWS = 64, 128, 8
-(OP_CONST, OP_LOAD, OP_AUX, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_POWI, OP_ABS, OP_SIN, OP_COS, OP_DIV) = range(12)
+(OP_CONST, OP_LOAD, OP_AUX, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_POWI, OP_ABS, OP_SIN, OP_COS, OP_DIV, OP_GRID2D) = range(13)
+MAX_GRIDS = 2
 
 
 class TdeLayer(C.Structure):
@@ -41,16 +42,22 @@ class TdeOp(C.Structure):
     _fields_ = [("op", C.c_int32), ("dst", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("imm", C.c_float)]
 
 
+class TdeGrid2D(C.Structure):
+    _fields_ = [("gx", C.c_void_p), ("gy", C.c_void_p), ("values", C.c_void_p), ("nx", C.c_int32), ("ny", C.c_int32)]
+
+
 class TdeLossProgram(C.Structure):
     _fields_ = [("n_ops", C.c_int32), ("n_rows", C.c_int32), ("ops", TdeOp * MAX_OPS),
                 ("res_reg", C.c_int32 * MAX_ROWS), ("w_aux", C.c_int32 * MAX_ROWS),
-                ("w_const", C.c_float * MAX_ROWS), ("coef", C.c_float * MAX_ROWS)]
+                ("w_const", C.c_float * MAX_ROWS), ("coef", C.c_float * MAX_ROWS),
+                ("w_reg", C.c_int32 * MAX_ROWS), ("n_grids", C.c_int32), ("reserved", C.c_int32),
+                ("grids", TdeGrid2D * MAX_GRIDS)]
 
 
 EXPORTS = ["tde_last_error", "tde_version", "tde_abi_struct_bytes", "tde_plan", "tde_jet_forward", "tde_jet_backward",
            "tde_residual_loss", "tde_adam_step", "tde_fp32_peak_probe", "tde_launch_count", "tde_profile_begin",
            "tde_profile_end", "tde_profile_kind", "tde_plan_paths", "tde_grid_interp2d", "tde_set_option",
-           "tde_jet_backward_range"]
+           "tde_jet_backward_range", "tde_residual_loss_points"]
 
 _LIB = None
 
@@ -65,6 +72,7 @@ def _declare(lib):
     lib.tde_jet_backward.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), vp, i64, vp, vp, i64, f32, vp, vp, vp]
     lib.tde_jet_backward_range.argtypes = [C.POINTER(TdeNet), C.POINTER(TdeJetSpec), vp, i64, vp, vp, i64, i64, i64, f32, vp, vp, vp]
     lib.tde_residual_loss.argtypes = [C.POINTER(TdeLossProgram), vp, i64, i32, vp, i64, i64, i64, f32, vp, vp, vp, vp, vp]
+    lib.tde_residual_loss_points.argtypes = [C.POINTER(TdeLossProgram), vp, i64, i32, vp, i64, i64, i64, vp, vp, vp]
     lib.tde_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, i32, vp]
     lib.tde_fp32_peak_probe.argtypes = [C.POINTER(C.c_double), vp]
     lib.tde_profile_begin.argtypes = []

@@ -622,6 +622,40 @@ __global__ void reduce_grads_kernel(const __grid_constant__ ReduceArgs a, const 
     flat[i] += a.scale * s;
 }
 
+// bilinear grid lookup pieces (GridInterpolator.py:50-83), shared by tde_grid_interp2d and the loss kernel's GRID2D op
+template <bool SMEM>
+__device__ __forceinline__ float grid_at(const float* g, const int i) { return SMEM ? g[i] : __ldg(g + i); }
+template <bool SMEM>
+__device__ __forceinline__ void grid_bracket(const float* g, const int n, const float x, int& il, int& ir, float& dl, float& dr) {
+    int lo = 0, hi = n;                       // first index with g[i] >= x  (torch.bucketize, right = false)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (grid_at<SMEM>(g, mid) < x) lo = mid + 1; else hi = mid;
+    }
+    ir = lo < n ? lo : n - 1;
+    il = ir - 1 < 0 ? 0 : ir - 1;
+    dl = x - grid_at<SMEM>(g, il);
+    dr = grid_at<SMEM>(g, ir) - x;
+    if (dl < 0.0f) dl = 0.0f;
+    if (dr < 0.0f) dr = 0.0f;
+    if (dl == 0.0f && dr == 0.0f) dl = dr = 1.0f;
+}
+// one lookup, corner order and weights as in the reference: value[left/right] * distance to the OTHER side
+template <bool SMEM>
+__device__ __forceinline__ float grid_lookup(const float* sx, const int nx, const float* sy, const int ny,
+                                             const float* __restrict__ values, const float x, const float y) {
+    int xl, xr, yl, yr;
+    float dxl, dxr, dyl, dyr;
+    grid_bracket<SMEM>(sx, nx, x, xl, xr, dxl, dxr);
+    grid_bracket<SMEM>(sy, ny, y, yl, yr, dyl, dyr);
+    float num = 0.0f;
+    num += __ldg(values + (int64_t)xl * ny + yl) * (dxr * dyr);
+    num += __ldg(values + (int64_t)xl * ny + yr) * (dxr * dyl);
+    num += __ldg(values + (int64_t)xr * ny + yl) * (dxl * dyr);
+    num += __ldg(values + (int64_t)xr * ny + yr) * (dxl * dyl);
+    return num / ((dxl + dxr) * (dyl + dyr));
+}
+
 // ---------------------------------------------------------------------------------------------
 // fused residual + loss: register-program interpreter, forward then reverse sweep per point
 // ---------------------------------------------------------------------------------------------
@@ -639,7 +673,7 @@ __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
     const __grid_constant__ TdeLossProgram prog, const float* __restrict__ streams, int64_t ld, int n_stream_rows,
     const float* __restrict__ aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
     const float* __restrict__ coef_dev, float* __restrict__ row_sums, float* __restrict__ seeds,
-    float* __restrict__ point_res, const int slot) {
+    float* __restrict__ point_res, float* __restrict__ point_w, const int slot) {
     __shared__ float red[TDE_MAX_ROWS][kLossThreads / 32];
     __shared__ bool is_last;
     float part[TDE_MAX_ROWS], coef[TDE_MAX_ROWS];
@@ -674,6 +708,10 @@ __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
                 case TDE_OP_SIN: r = sinf(v[op.a]); break;
                 case TDE_OP_COS: r = cosf(v[op.a]); break;
                 case TDE_OP_DIV: r = v[op.a] / v[op.b]; break;
+                case TDE_OP_GRID2D: {
+                    const TdeGrid2D& gd = prog.grids[(int)op.imm];
+                    r = grid_lookup<false>(gd.gx, gd.nx, gd.gy, gd.ny, gd.values, v[op.a], v[op.b]);
+                } break;
                 default: r = 0.0f;
             }
             v[op.dst] = r;
@@ -681,10 +719,12 @@ __global__ void __launch_bounds__(kLossThreads) residual_loss_kernel(
         }
         for (int r = 0; r < prog.n_rows; ++r) {
             const float res = v[prog.res_reg[r]];
-            const float w = prog.w_aux[r] >= 0 ? aux[(int64_t)prog.w_aux[r] * ld_aux + i] : prog.w_const[r];
+            const float w = prog.w_reg[r] >= 0 ? v[prog.w_reg[r]]
+                            : (prog.w_aux[r] >= 0 ? aux[(int64_t)prog.w_aux[r] * ld_aux + i] : prog.w_const[r]);
             part[r] += w * res * res;
             adj[prog.res_reg[r]] += coef[r] * inv_count * 2.0f * w * res;
             if (point_res) point_res[(int64_t)r * n + i] = res;
+            if (point_w) point_w[(int64_t)r * n + i] = w;
         }
         if (seeds) {
             for (int s = 0; s < n_stream_rows; ++s) seeds[(int64_t)s * ld + p] = 0.0f;
@@ -793,23 +833,6 @@ __global__ void __launch_bounds__(512) ffma_probe_kernel(float* out, int iters, 
 // bilinear grid lookup (GridInterpolator.py:50-83), one thread per query point
 // ---------------------------------------------------------------------------------------------
 namespace {
-template <bool SMEM>
-__device__ __forceinline__ float grid_at(const float* g, const int i) { return SMEM ? g[i] : __ldg(g + i); }
-template <bool SMEM>
-__device__ __forceinline__ void grid_bracket(const float* g, const int n, const float x, int& il, int& ir, float& dl, float& dr) {
-    int lo = 0, hi = n;                       // first index with g[i] >= x  (torch.bucketize, right = false)
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (grid_at<SMEM>(g, mid) < x) lo = mid + 1; else hi = mid;
-    }
-    ir = lo < n ? lo : n - 1;
-    il = ir - 1 < 0 ? 0 : ir - 1;
-    dl = x - grid_at<SMEM>(g, il);
-    dr = grid_at<SMEM>(g, ir) - x;
-    if (dl < 0.0f) dl = 0.0f;
-    if (dr < 0.0f) dr = 0.0f;
-    if (dl == 0.0f && dr == 0.0f) dl = dr = 1.0f;
-}
 // SMEM: the two coordinate arrays are staged in shared memory (the binary searches are 2 x log2(n) dependent loads per point)
 template <bool SMEM>
 __global__ void grid_interp2d_kernel(const float* __restrict__ gx, const int nx, const float* __restrict__ gy, const int ny,
@@ -826,17 +849,7 @@ __global__ void grid_interp2d_kernel(const float* __restrict__ gx, const int nx,
         sy = grid_s + nx;
     }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int xl, xr, yl, yr;
-        float dxl, dxr, dyl, dyr;
-        grid_bracket<SMEM>(sx, nx, __ldcs(x + i), xl, xr, dxl, dxr);
-        grid_bracket<SMEM>(sy, ny, __ldcs(y + i), yl, yr, dyl, dyr);
-        // corner order and weights as in the reference: value[left/right] * distance to the OTHER side
-        float num = 0.0f;
-        num += __ldg(values + (int64_t)xl * ny + yl) * (dxr * dyr);
-        num += __ldg(values + (int64_t)xl * ny + yr) * (dxr * dyl);
-        num += __ldg(values + (int64_t)xr * ny + yl) * (dxl * dyr);
-        num += __ldg(values + (int64_t)xr * ny + yr) * (dxl * dyl);
-        __stcs(out + i, num / ((dxl + dxr) * (dyl + dyr)));
+        __stcs(out + i, grid_lookup<SMEM>(sx, nx, sy, ny, values, __ldcs(x + i), __ldcs(y + i)));
     }
 }
 }  // namespace
@@ -1060,11 +1073,37 @@ int tde_jet_backward_range(const TdeNet* net, const TdeJetSpec* spec, const floa
                          flat_grad, (float*)workspace, (cudaStream_t)stream);
 }
 
+static int launch_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
+                                const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
+                                const float* coef_dev, float* row_sums, float* seeds, float* point_res, float* point_w, void* stream);
+
 int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
                       const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
                       const float* coef_dev, float* row_sums, float* seeds, float* point_res, void* stream) {
-    if (!prog || !streams) return fail("null program/streams");
     if (!row_sums && !seeds && !point_res) return fail("nothing to compute: row_sums, seeds and point_res are all null");
+    return launch_residual_loss(prog, streams, ld, n_stream_rows, aux, ld_aux, p0, n, inv_count, coef_dev, row_sums, seeds, point_res,
+                                nullptr, stream);
+}
+
+int tde_residual_loss_points(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
+                             const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float* point_res, float* point_w,
+                             void* stream) {
+    if (!point_res && !point_w) return fail("nothing to compute: point_res and point_w are both null");
+    return launch_residual_loss(prog, streams, ld, n_stream_rows, aux, ld_aux, p0, n, 1.0f, nullptr, nullptr, nullptr, point_res,
+                                point_w, stream);
+}
+
+static int launch_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t ld, int32_t n_stream_rows,
+                                const float* aux, int64_t ld_aux, int64_t p0, int64_t n, float inv_count,
+                                const float* coef_dev, float* row_sums, float* seeds, float* point_res, float* point_w, void* stream) {
+    if (!prog || !streams) return fail("null program/streams");
+    if (prog->n_grids < 0 || prog->n_grids > TDE_MAX_GRIDS) return fail("n_grids %d out of range", prog->n_grids);
+    for (int gi = 0; gi < prog->n_grids; ++gi) {
+        const TdeGrid2D& gd = prog->grids[gi];
+        if (!gd.gx || !gd.gy || !gd.values || gd.nx < 1 || gd.ny < 1) return fail("grid %d: null pointer or empty axis", gi);
+    }
+    for (int r = 0; r < prog->n_rows && r < TDE_MAX_ROWS; ++r)
+        if (prog->w_reg[r] >= TDE_MAX_REGS) return fail("row %d: weight register %d out of range", r, prog->w_reg[r]);
     if (prog->n_ops < 1 || prog->n_ops > TDE_MAX_OPS) return fail("n_ops %d out of range", prog->n_ops);
     if (prog->n_rows < 1 || prog->n_rows > TDE_MAX_ROWS) return fail("n_rows %d out of range", prog->n_rows);
     for (int k = 0; k < prog->n_ops; ++k) {
@@ -1072,12 +1111,14 @@ int tde_residual_loss(const TdeLossProgram* prog, const float* streams, int64_t 
         if (op.dst < 0 || op.dst >= TDE_MAX_REGS) return fail("op %d: dst register %d out of range", k, op.dst);
         if (op.op == TDE_OP_LOAD && (op.a < 0 || op.a >= n_stream_rows)) return fail("op %d: stream row %d out of range", k, op.a);
         if (op.op == TDE_OP_AUX && !aux) return fail("op %d reads aux but aux is null", k);
+        if (op.op == TDE_OP_GRID2D && ((int)op.imm < 0 || (int)op.imm >= prog->n_grids)) return fail("op %d: grid %d out of range", k, (int)op.imm);
+        if (op.op == TDE_OP_GRID2D && (op.b < 0 || op.b >= TDE_MAX_REGS)) return fail("op %d: source register out of range", k);
         if (op.op >= TDE_OP_ADD && (op.a < 0 || op.a >= TDE_MAX_REGS)) return fail("op %d: source register out of range", k);
     }
     if (n == 0) return 0;
     const int blocks = (int)std::min<int64_t>((n + kLossThreads - 1) / kLossThreads, kLossBlocks);
     residual_loss_kernel<<<blocks, kLossThreads, 0, (cudaStream_t)stream>>>(*prog, streams, ld, n_stream_rows, aux, ld_aux,
-                                                                             p0, n, inv_count, coef_dev, row_sums, seeds, point_res,
+                                                                             p0, n, inv_count, coef_dev, row_sums, seeds, point_res, point_w,
                                                                              (int)(g_loss_seq++ % kLossSlots));
     ++g_launches;
     TDE_CUDA(cudaGetLastError());

@@ -26,6 +26,7 @@ class Sym:
     __slots__ = ('op', 'args', 'imm', 'key')
     _BIN = {'add': _lib.OP_ADD, 'sub': _lib.OP_SUB, 'mul': _lib.OP_MUL, 'div': _lib.OP_DIV}
     _UN = {'neg': _lib.OP_NEG, 'abs': _lib.OP_ABS, 'sin': _lib.OP_SIN, 'cos': _lib.OP_COS, 'powi': _lib.OP_POWI}
+    # 'grid2d': (x, y) -> bilinear lookup in the grid registered under slot `imm` (RegularGridInterpolator called on Syms)
 
     def __init__(self, op, args=(), imm=None):
         self.op, self.args, self.imm = op, tuple(args), imm
@@ -104,9 +105,20 @@ class Sym:
 
 
 class _TraceContext:
-    """Tensor scalars met while tracing one group: each becomes the aux leaf '__s<k>' that is re-read every launch."""
+    """Tensor scalars met while tracing one group: each becomes the aux leaf '__s<k>' that is re-read every launch.
+    Grid interpolators called on traced coordinates get a slot in the program's grid table."""
     def __init__(self):
         self.scalars: List[torch.Tensor] = []
+        self.grids: list = []
+
+    def grid_slot(self, interp) -> int:
+        for k, g in enumerate(self.grids):
+            if g is interp:
+                return k
+        if len(self.grids) >= _lib.MAX_GRIDS:
+            raise TraceError('too many distinct grid fields in one group')
+        self.grids.append(interp)
+        return len(self.grids) - 1
 
     def scalar_slot(self, t: torch.Tensor) -> str:
         for k, u in enumerate(self.scalars):
@@ -142,7 +154,8 @@ class _Guard:
 
 class GroupProgram:
     """Compiled rows of one group."""
-    def __init__(self, group_name: str, row_ids: List[int], res_syms: List[Sym], stream_row: Dict[str, int], n_stream_rows: int):
+    def __init__(self, group_name: str, row_ids: List[int], res_syms: List[Sym], stream_row: Dict[str, int], n_stream_rows: int,
+                 weight_syms: Optional[List[Optional[Sym]]] = None):
         self.group = group_name
         self.row_ids = row_ids
         self.aux_names: List[str] = []
@@ -165,6 +178,9 @@ class GroupProgram:
             elif node.op in Sym._BIN:
                 a, b = emit(node.args[0]), emit(node.args[1])
                 rec = (Sym._BIN[node.op], a, b, 0.0)
+            elif node.op == 'grid2d':
+                a, b = emit(node.args[0]), emit(node.args[1])
+                rec = (_lib.OP_GRID2D, a, b, node.imm)
             else:
                 a = emit(node.args[0])
                 rec = (Sym._UN[node.op], a, 0, node.imm or 0.0)
@@ -180,15 +196,35 @@ class GroupProgram:
         for i, s in enumerate(res_syms):
             prog.res_reg[i] = emit(s)
             prog.w_aux[i] = -1
+            prog.w_reg[i] = -1
             prog.w_const[i] = 1.0
             prog.coef[i] = 1.0
+        self.traced_weight = [False] * len(res_syms)      # rows whose weighting function runs inside the kernel
+        for i, w in enumerate(weight_syms or []):
+            if w is not None:
+                prog.w_reg[i] = emit(w)
+                self.traced_weight[i] = True
         prog.n_ops, prog.n_rows = len(ops), len(res_syms)
         for k, (op, dst, a, b, imm) in enumerate(ops):
             prog.ops[k].op, prog.ops[k].dst, prog.ops[k].a, prog.ops[k].b, prog.ops[k].imm = op, dst, a, b, imm
         self.prog = prog
         self.weight_aux: List[Optional[int]] = [None] * len(res_syms)
         self.scalars: List[torch.Tensor] = []          # tensor scalars behind the '__s<k>' aux rows
-        self.signature = tuple(s.key for s in res_syms)   # structure + baked Python constants of the traced rows
+        self.grids: list = []                          # interpolators behind the GRID2D slots
+        self._grid_keep = []                           # device tensors the grid table points at
+        self.signature = None                          # set by trace_group: what the rows traced to (see signature_of)
+
+    def bind_grids(self, device) -> None:
+        """(Re)fill the program's grid table with device pointers (the interpolator may have been moved / re-valued)."""
+        self.prog.n_grids = len(self.grids)
+        keep = []
+        for k, g in enumerate(self.grids):
+            gx, gy = (p.to(device=device, dtype=torch.float32).contiguous() for p in g.points)
+            vals = g.values.to(device=device, dtype=torch.float32).contiguous()
+            keep += [gx, gy, vals]
+            e = self.prog.grids[k]
+            e.gx, e.gy, e.values, e.nx, e.ny = gx.data_ptr(), gy.data_ptr(), vals.data_ptr(), gx.shape[0], gy.shape[0]
+        self._grid_keep = keep
 
     def _aux(self, name: str) -> int:
         if name not in self.aux_names:
@@ -205,10 +241,23 @@ class GroupProgram:
 
 def trace_group(group, rows: List[dict], stream_row: Dict[str, int], n_stream_rows: int) -> GroupProgram:
     """rows: Loss_handler records of ONE group (non-custom). Raises TraceError if any row cannot be fused."""
-    syms, ctx = trace_rows(group, rows, stream_row)
-    prog = GroupProgram(getattr(group, 'name', None), list(range(len(rows))), syms, stream_row, n_stream_rows)
+    syms, wsyms, ctx = trace_rows(group, rows, stream_row)
+    prog = GroupProgram(getattr(group, 'name', None), list(range(len(rows))), syms, stream_row, n_stream_rows, wsyms)
     prog.scalars = ctx.scalars
+    prog.grids = ctx.grids
+    prog.signature = _signature(syms, wsyms, ctx)
     return prog
+
+
+def _signature(syms, wsyms, ctx) -> tuple:
+    return (tuple(s.key for s in syms), tuple(w.key if w is not None else None for w in wsyms), tuple(id(g) for g in ctx.grids))
+
+
+def grid_lookup(interp, x, y) -> Sym:
+    """RegularGridInterpolator(x, y) on traced coordinates: one GRID2D op instead of a separate lookup launch + aux row."""
+    if _TRACE is None:
+        raise TraceError('grid lookup outside a trace')
+    return Sym('grid2d', (Sym.lift(x), Sym.lift(y)), imm=float(_TRACE.grid_slot(interp)))
 
 
 def trace_rows(group, rows: List[dict], stream_row: Dict[str, int]):
@@ -219,16 +268,32 @@ def trace_rows(group, rows: List[dict], stream_row: Dict[str, int]):
     prev, _TRACE = _TRACE, _TraceContext()
     try:
         syms = [Sym.lift(spec['evaluation'](gp, outs)) for spec in rows]
-        return syms, _TRACE
+        wsyms = [trace_weight(spec, gp, outs) for spec in rows]
+        return syms, wsyms, _TRACE
     finally:
         _TRACE = prev
+
+
+def trace_weight(spec: dict, gp, outs) -> Optional[Sym]:
+    """The row's weighting function as a Sym of the group's input coordinates (an SDF lookup, `1 - 10 |x|`, ...), or None:
+    constants, per-point tensors and anything that does not trace keep the aux-row / constant path (eval_weight)."""
+    w = spec.get('weighting_spec', 1)
+    if not callable(w):
+        return None
+    guard = {k: _Guard() for k in outs}
+    try:
+        val = spec['weighting_function'](gp, guard)
+    except TraceError:
+        return None
+    except Exception:       # noqa: BLE001 - a weighting written for tensors only (torch.where, indexing ...): evaluate it with torch
+        return None
+    return val if isinstance(val, Sym) and val.op != 'const' else None
 
 
 def signature_of(group, rows: List[dict], stream_row: Dict[str, int]) -> tuple:
     """Signature of what the rows trace to NOW: differs from a cached program's when a Python number captured by a residual
     closure (or a group's unbatchable) changed since that program was compiled."""
-    syms, _ = trace_rows(group, rows, stream_row)
-    return tuple(s.key for s in syms)
+    return _signature(*trace_rows(group, rows, stream_row))
 
 
 def eval_weight(spec: dict, group, out_names) -> object:
@@ -292,3 +357,18 @@ class _FusedRows(torch.autograd.Function):
 
 def fused_rows(block: torch.Tensor, launches) -> torch.Tensor:
     return _FusedRows.apply(block, launches)
+
+
+def point_rows(block: torch.Tensor, gp: GroupProgram, aux, lo: int, n: int):
+    """(residuals[n_rows, n], weights[n_rows, n]) of one fused group: the per-point quantities `Loss.point_error()` /
+    `weighted_point_error()` and `R3_sampler` read (utils/loss.py:33-52, utils/sampling.py:70-112).  One forward-only launch
+    of the loss kernel; nothing is kept for autograd (these feed samplers and diagnostics)."""
+    res = torch.empty((gp.prog.n_rows, n), dtype=torch.float32, device=block.device)
+    wts = torch.empty_like(res)
+    if n > 0:
+        with _lib.on_device(block.device):
+            rc = _lib.lib().tde_residual_loss_points(C.byref(gp.prog), block.data_ptr(), block.shape[1], gp.n_stream_rows,
+                                                     aux.data_ptr() if aux is not None else None, n, lo, n, res.data_ptr(),
+                                                     wts.data_ptr(), torch.cuda.current_stream(block.device).cuda_stream)
+        _lib.check(rc, 'tde_residual_loss_points')
+    return res, wts

@@ -40,11 +40,20 @@ class Loss:
     def error_func(self, r: Tensor) -> Tensor:
         return torch.abs(r).pow(self.power) if self.power is not None else r
 
+    def _materialise_points(self, row):
+        """Rows reduced by the fused kernel keep no per-point tensors; the first request launches the kernel's point pass for
+        the row's whole group (tde_residual_loss_points) and fills residual + weighting of every row of that group.  These
+        are detached values for samplers and diagnostics (R3_sampler, Causal_weighting), as in sampling.py:89 `no_grad`."""
+        if row.get('residual') is None and row.get('_points') is not None:
+            res, wts, rows_of_group = row['_points']()
+            for i, r in enumerate(rows_of_group):
+                r['residual'], r['weighting'] = res[i], wts[i]
+
     def point_error(self) -> List[Tensor]:
         for row in self.losses:
+            self._materialise_points(row)
             if row.get('residual') is None:
-                raise RuntimeError("per-point residuals are not materialised by the fused loss kernel; "
-                                   "call Loss_handler.calculate(..., fused=False) when they are needed")
+                raise RuntimeError("per-point residuals of this row are not available")
             if row.get('point_error') is None:
                 row['point_error'] = self.error_func(row['residual'])
         return [row['point_error'] for row in self.losses]
@@ -55,6 +64,12 @@ class Loss:
             if row.get('weighted_error') is None:
                 row['weighted_error'] = row['weighting'] * row['point_error']
         return [row['weighted_error'] for row in self.losses]
+
+    def residual_rows(self, group: str, weighted: bool = True) -> List[Tensor]:
+        """Per-point (weighted) errors of the 'residual' rows of one group, in table order: what the reference's R3_sampler
+        looks up as `table['Residual'][group]` (utils/sampling.py:72-76)."""
+        errs = self.weighted_point_error() if weighted else self.point_error()
+        return [e for e, row in zip(errs, self.losses) if row['group'] == group and str(row['loss_type']).lower() == 'residual']
 
     def aggregated_loss(self) -> List[Tensor]:
         if not self._done:
@@ -145,6 +160,7 @@ class Loss_handler:
         ranges = getattr(batched_output, 'ranges', None) or {}
         n_all = block.shape[1] if block is not None else 0
         rows = []
+        group_rows: Dict[str, list] = {}
         for spec in self.rows:
             src = None if block is None else (block, (0, n_all) if spec['custom'] else ranges.get(spec['group']))
             if src is not None and src[1] is None:
@@ -155,6 +171,9 @@ class Loss_handler:
                 row['residual'] = None
                 row['weighting'] = None
                 row['aggregated_loss'] = fused_groups[spec['group']].pop(0)
+                mine = group_rows.setdefault(spec['group'], [])
+                mine.append(row)
+                row['_points'] = self._point_pass(block, self._launched[spec['group']], mine)
                 rows.append(row)
                 continue
             row = dict(spec)
@@ -172,6 +191,19 @@ class Loss_handler:
             rows.append(row)
         return Loss(rows, aggregation_method, power)
 
+    @staticmethod
+    def _point_pass(block, launch, rows_of_group):
+        """Closure that runs the loss kernel's point pass for one fused group once and caches the result."""
+        cache = []
+
+        def run():
+            if not cache:
+                gp, aux, lo, n = launch
+                with torch.no_grad():
+                    cache.append(FL.point_rows(block.detach(), gp, aux, lo, n))
+            return cache[0][0], cache[0][1], rows_of_group
+        return run
+
     # -- fused path ---------------------------------------------------------------------------
     def _fused_rows(self, batched_input, out) -> Dict[str, list]:
         """Launch the fused kernel for every group whose rows trace into a register program.
@@ -179,6 +211,7 @@ class Loss_handler:
         names = list(out.stream_row.keys())
         n_stream_rows = out.block.shape[0]
         launches, owners = [], []
+        self._launched = {}
         for g, (lo, hi) in out.ranges.items():
             specs = [r for r in self.rows if r['group'] == g and not r['custom']]
             if not specs or g not in batched_input:
@@ -187,13 +220,15 @@ class Loss_handler:
             key = (g, tuple(names), len(specs))
             gp = self._programs.get(key)
             try:
-                weights = [FL.eval_weight(sp, group, names) for sp in specs]
+                # rows whose weighting function was traced into the program (SDF lookup and the like) need no torch evaluation
+                weights = [None if gp and gp.traced_weight[i] else FL.eval_weight(sp, group, names) for i, sp in enumerate(specs)]
                 if gp and self.revalidate and FL.signature_of(group, specs, out.stream_row) != gp.signature:
                     gp = None      # a Python constant behind a residual closure changed: compile the rows again
+                    weights = [FL.eval_weight(sp, group, names) for sp in specs]
                 if gp is None:
                     gp = FL.trace_group(group, specs, out.stream_row, n_stream_rows)
                     for i, w in enumerate(weights):
-                        if isinstance(w, torch.Tensor):
+                        if isinstance(w, torch.Tensor) and not gp.traced_weight[i]:
                             gp.weight_slot(i)
                     self._programs[key] = gp
                     self.fusion_report[g] = 'fused'
@@ -217,11 +252,14 @@ class Loss_handler:
                         cols.append(group.batchables[a].to(torch.float32))
                 aux = torch.stack(cols).contiguous()
             for i, w in enumerate(weights):
-                if gp.weight_aux[i] is None:
+                if gp.weight_aux[i] is None and not gp.traced_weight[i]:
                     if isinstance(w, torch.Tensor):
                         raise RuntimeError(f"weighting of group '{g}' changed from a constant to a per-point tensor")
                     gp.prog.w_const[i] = float(w)
+            if gp.grids:
+                gp.bind_grids(out.block.device)
             launches.append((gp, aux, lo, n))
+            self._launched[g] = launches[-1]
             owners.append((g, gp.prog.n_rows))
         if not launches:
             return {}

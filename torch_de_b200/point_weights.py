@@ -47,6 +47,11 @@ class RegularGridInterpolator:
         self.device = device
 
     def __call__(self, x, y: torch.Tensor, **kwargs):
+        from . import fused_loss as FL
+        if isinstance(x, FL.Sym) or isinstance(y, FL.Sym):
+            # called by the loss tracer on symbolic coordinates (a weighting such as DE_func(domain.create_sdf()),
+            # Stokes_Cylinder.py:34,79): the lookup becomes one op of the fused loss kernel instead of a launch + an aux row
+            return FL.grid_lookup(self, x, y)
         return self.interpolate([x, y])
 
     def interpolate(self, points_to_interp):
@@ -95,15 +100,22 @@ class R3_sampler:
         return total.to(device)
 
     def _residual_rows(self, res, loss_type):
-        if not (hasattr(res, 'weighted_error') and hasattr(res, 'point_error')):
-            return res                                        # already an iterable of per-point residual vectors
-        if loss_type == 'weighted':
-            table = res.weighted_error()
-        elif loss_type == 'point error':
-            table = res.point_error()
-        else:
+        if not hasattr(res, 'residual_rows'):
+            if not (hasattr(res, 'weighted_error') and hasattr(res, 'point_error')):
+                return res                                    # already an iterable of per-point residual vectors
+            # an object with the table accessors the reference's sampler calls (sampling.py:72-76)
+            if loss_type not in ('weighted', 'point error'):
+                raise ValueError('loss_type accepts only strings weighted and point error')
+            table = res.weighted_error() if loss_type == 'weighted' else res.point_error()
+            return list(table['Residual'][self.group].values())
+        if loss_type not in ('weighted', 'point error'):
             raise ValueError('loss_type accepts only strings weighted and point error')
-        return list(table['Residual'][self.group].values())
+        # a Loss object: the 'residual' rows of my group (sampling.py:72-76); under the fused loss path the per-point values
+        # come from the loss kernel's point pass
+        rows = res.residual_rows(self.group, weighted=loss_type == 'weighted')
+        if not rows:
+            raise KeyError(f"the loss table has no 'residual' rows for group {self.group!r}")
+        return rows
 
     def retain(self, x, Res, mean):
         return x[Res >= mean]
