@@ -26,6 +26,8 @@ struct TcBwdParams {
     int d_in, n_out, L, W, act, MB;
     int n_stages, n_acc, fourier_half;
     int pair;                   // W = 256: use the CTA-pair kernel
+    int dbg;                    // bit 4: weight copies without the L2 evict-last hint (A/B measurement)
+    int stage_dbuf;             // shared memory has room for a second (x | seeds) staging buffer: the next tile's is fetched early
     int first_in[TDE_MAX_FIRST];
     const float* wct;           // transposed-weight chunk images [(L-1)][W/8][chunk]
     const float* w_out;         // [n_out][W] packed
@@ -67,12 +69,12 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_backward_tc_kernel(
     constexpr uint32_t z_planes = (uint32_t)(W / 32) * P::kAtom;
     constexpr uint32_t chunk_bytes = (uint32_t)KSC * 8192u;
     unsigned char* wst = zpl + z_planes;
-    float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
-    float* xs = wout_s + p.n_out * W;                 // [PTS][d_in]
-    float* seeds_s = xs + PTS * p.d_in;               // [PTS points][J channels][4 outputs (padded)]: one float4 per point and channel
+    // x and the seeds of a tile are staged twice over: the NEXT tile's are fetched while this tile's layers run
+    float* const xs_buf = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);       // 2 x { x [PTS][d_in] | seeds [PTS points][J channels][4 outputs (padded)] }
+    const int stage_floats = PTS * p.d_in + J * TDE_MAX_OUT * PTS;
     static_assert(TDE_MAX_OUT == 4, "seed rows are staged as float4 per channel");
-    // barriers at the tail (same carve-up as the forward kernel: [planes][stages][w_out][x][seeds | y][4 floats][barriers])
-    uint64_t* full = reinterpret_cast<uint64_t*>(seeds_s + J * TDE_MAX_OUT * PTS + 4);
+    // barriers at the tail (same carve-up as the forward kernel: [planes][stages][2 x (x | seeds)][4 floats][barriers])
+    uint64_t* full = reinterpret_cast<uint64_t*>(xs_buf + (p.stage_dbuf ? 2 : 1) * stage_floats + 4);
     uint64_t* empty = full + kTcMaxStages;
     uint64_t* act_ready = empty + kTcMaxStages;
     uint64_t* acc_ready = act_ready + kTcMaxBlocks;     // [neuron block]
@@ -117,14 +119,20 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_backward_tc_kernel(
             int s = 0;
             uint32_t ph = 0;
             const uint32_t part = chunk_bytes / kTcCluster;
+            const uint64_t pol = l2_policy_evict_last();
+            const bool hint = !(p.dbg & 16);
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
                 for (int l = p.L - 1; l >= 1; --l) {
                     const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wct) + (size_t)(l - 1) * n_ks * chunk_bytes;
                     for (int ks = 0; ks < n_ks; ++ks) {
                         mbar_wait(&empty[s], ph ^ 1);
                         mbar_expect_tx(&full[s], chunk_bytes);
-                        bulk_g2s_mc(wst + (size_t)s * chunk_bytes + crank * part, src + (size_t)ks * chunk_bytes + crank * part, part,
-                                    &full[s], (uint16_t)((1u << kTcCluster) - 1));
+                        if (hint)
+                            bulk_g2s_mc_hint(wst + (size_t)s * chunk_bytes + crank * part, src + (size_t)ks * chunk_bytes + crank * part, part,
+                                             &full[s], (uint16_t)((1u << kTcCluster) - 1), pol);
+                        else
+                            bulk_g2s_mc(wst + (size_t)s * chunk_bytes + crank * part, src + (size_t)ks * chunk_bytes + crank * part, part,
+                                        &full[s], (uint16_t)((1u << kTcCluster) - 1));
                         if (++s == n_stages) {
                             s = 0;
                             ph ^= 1;
@@ -167,7 +175,6 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_backward_tc_kernel(
             const int et = e * 32 + lane;
             auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory"); };
 
-            for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
             const uint32_t hoff = P::template hi_off<kAccSets>((uint32_t)n0 >> 5);
             const uint32_t zrow = (uint32_t)(n0 >> 5) * P::kAtom + hoff + (uint32_t)(n0 & 3) * 4u;
             const uint32_t lo_delta = P::kHalf - 2u * hoff;
@@ -185,56 +192,77 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_backward_tc_kernel(
             float* gp_hi = gp + p.gp_dup_hi[pg];      // b_hidden | w_out
             uint32_t acc_ph = 0;
 
-            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
-                const bool first = pair == first_pair;
-                // the second tile of the last pair may be padding (>= n_tiles): x = 0 and seeds = 0 there and the streams have
-                // rows for it, so it runs the same code and contributes exact zeros
-                const int64_t tile = pair * kTcCluster + crank;
+            constexpr int GC = kTcGroup * J;
+            constexpr int NG2 = PPV / kTcGroup;       // 4-point steps per visit
+            // global -> shared staging of one tile's points and seeds (a padding tile gets zeros)
+            auto stage_tile = [&](const int64_t tile, float* xs_b) {
                 const int64_t pbase = tile * PTS;
-                const bool tstamp = p.dbg_buf && blockIdx.x == 0 && et == 0 && pair == first_pair + 3 * pair_step;
-                if (tstamp) p.dbg_buf[40] = clock64();      // tile start
+                float* seeds_b = xs_b + PTS * p.d_in;
                 for (int i = et; i < PTS * p.d_in; i += n_epi) {
                     const int64_t gpt = pbase + i / p.d_in;
-                    xs[i] = gpt < p.B ? p.x[gpt * p.d_in + (i % p.d_in)] : 0.0f;
+                    xs_b[i] = gpt < p.B ? p.x[gpt * p.d_in + (i % p.d_in)] : 0.0f;
                 }
                 for (int i = et; i < J * TDE_MAX_OUT * PTS; i += n_epi) {       // coalesced over the points of a seed row
                     const int r = i / PTS, pt = i - r * PTS;          // r = channel * 4 + output
                     const int c = r >> 2, o = r & 3;
                     const int64_t gpt = pbase + pt;
-                    seeds_s[(pt * J + c) * 4 + o] = (o < p.n_out && gpt < p.B) ? p.seeds[(size_t)(c * p.n_out + o) * p.ld_seeds + gpt] : 0.0f;
+                    seeds_b[(pt * J + c) * 4 + o] = (o < p.n_out && gpt < p.B) ? p.seeds[(size_t)(c * p.n_out + o) * p.ld_seeds + gpt] : 0.0f;
                 }
-                epi_sync();
-                if (tstamp) p.dbg_buf[41] = clock64();      // inputs staged
-                const size_t row0 = ((size_t)tile * N + (size_t)pg * (PPV * J)) * W + n0;     // [layer][tile][jet column][neuron]
+            };
+            auto row_of = [&](const int64_t tile) { return ((size_t)tile * N + (size_t)pg * (PPV * J)) * W + n0; };   // [layer][tile][jet column][neuron]
+            // all of this thread's stash values of a layer (every visit) are requested well before they are used, so their
+            // latency hides under the MMAs (a later prefetch would share a scoreboard with younger loads and stall).  Streaming
+            // loads (evict-first in L1 and L2: the weight images must stay L2-resident next to 40 GB of stash / Hbar traffic).
+            float stv[n_visits][NG2][GC];
+            auto load_stash = [&](const int l, const size_t row0) {
+                const float* srow = p.stash + (size_t)l * p.stash_layer_stride + row0;
+                asm volatile("" : "+l"(srow));
+#pragma unroll
+                for (int v = 0; v < n_visits; ++v)
+#pragma unroll
+                    for (int g = 0; g < NG2; ++g)
+#pragma unroll
+                        for (int i = 0; i < GC; ++i) stv[v][g][i] = __ldcs(srow + (size_t)(g * GC + i) * W + v * 128);
+            };
+            // my neurons' rows of w_out (read through L1; shared memory has no room for it next to a fourth weight stage)
+            float wo_v[n_visits][TDE_MAX_OUT];
+#pragma unroll
+            for (int v = 0; v < n_visits; ++v)
+#pragma unroll
+                for (int o = 0; o < TDE_MAX_OUT; ++o) wo_v[v][o] = o < p.n_out ? __ldg(p.w_out + o * W + n0 + v * 128) : 0.0f;
+            int cur = 0;
+            if (first_pair < n_pairs) {
+                load_stash(p.L - 1, row_of(first_pair * kTcCluster + crank));
+                stage_tile(first_pair * kTcCluster + crank, xs_buf);
+            }
+            epi_sync();
+
+            for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
+                const bool first = pair == first_pair;
+                // the second tile of the last pair may be padding (>= n_tiles): x = 0 and seeds = 0 there and the streams have
+                // rows for it, so it runs the same code and contributes exact zeros
+                const int64_t tile = pair * kTcCluster + crank;
+                const bool has_next = pair + pair_step < n_pairs;
+                const int64_t next_tile = (pair + pair_step) * kTcCluster + crank;
+                const bool tstamp = p.dbg_buf && blockIdx.x == 0 && et == 0 && pair == first_pair + 3 * pair_step;
+                if (tstamp) p.dbg_buf[40] = clock64();      // tile start
+                const float* xs = xs_buf + cur * stage_floats;
+                const float* seeds_s = xs + PTS * p.d_in;
+                if (tstamp) p.dbg_buf[41] = clock64();      // inputs staged (by the previous iteration)
+                const size_t row0 = row_of(tile);
 
                 // Epilogue as 2 x (2 steps of 4 points): 8 points are unrolled so every shared/global offset is an immediate (a
                 // 16-point unroll is >200 KB of code and instruction-cache bound).  The stash values of the NEXT 4-point step
                 // are requested before the current step is processed; TMEM is read where it is used (12-cycle latency).
                 // Base addresses pass through empty asm statements: otherwise the compiler, short of registers, re-derives
                 // every one of the 240 addresses of a layer from the kernel parameters (10 instructions per store).
-                constexpr int GC = kTcGroup * J;
-                constexpr int NG2 = PPV / kTcGroup;       // 4-point steps per visit
-
                 // The body is instantiated three times (last hidden layer: adjoint seeded from the output layer; middle layers;
                 // input layer) so the hot middle-layer code carries none of the special-case registers or branches.
                 auto layer_body = [&](auto kind_c, const int l) {
                     constexpr int KIND = decltype(kind_c)::value;     // 2 last, 1 middle, 0 input layer
                     constexpr bool last = KIND == 2;
                     const size_t loff = (size_t)l * p.stash_layer_stride + row0;
-                    // all of this thread's stash values of the layer (every visit) are requested before the wait for the
-                    // accumulators, so their latency hides under the MMAs (a later prefetch would share a scoreboard with younger
-                    // loads and stall)
-                    float stv[n_visits][NG2][GC];
-                    {
-                        const float* srow = p.stash + loff;
-                        asm volatile("" : "+l"(srow));
-#pragma unroll
-                        for (int v = 0; v < n_visits; ++v)
-#pragma unroll
-                            for (int g = 0; g < NG2; ++g)
-#pragma unroll
-                                for (int i = 0; i < GC; ++i) stv[v][g][i] = __ldcs(srow + (size_t)(g * GC + i) * W + v * 128);
-                    }
+                    if (!last) load_stash(l, row0);      // (the last hidden layer's values were requested before the tile began)
                     static_for<n_visits>([&](auto v_c) {
                         constexpr int v = decltype(v_c)::value;
                         const int mb = own_mb + v, n = n0 + v * 128;
@@ -242,13 +270,14 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_backward_tc_kernel(
                         uint32_t zaddr[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) zaddr[j] = zaddr0[j] + (uint32_t)v * 4u * P::kAtom;
-                        const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && pg == 0 && pair == first_pair + 3 * pair_step && l >= 3 && l <= 5;
-                        long long* const dst = p.dbg_buf + 16 + ((5 - l) * 2 + (mb & 1)) * 4;   // steady-state tile, two neuron blocks
+                        const bool stamp = p.dbg_buf && blockIdx.x == 0 && (n & 127) == 0 && pg == 0 && pair == first_pair + 3 * pair_step && ((l >= 3 && l <= 5) || KIND != 1);
+                        // steady-state tile, two neuron blocks; slots 50.. / 58..: the last hidden layer (seeded from the output layer) / the input layer
+                        long long* const dst = p.dbg_buf + (KIND == 1 ? 16 + ((5 - l) * 2 + (mb & 1)) * 4 : (KIND == 2 ? 50 : 58) + (mb & 1) * 4);
                         if (stamp) dst[0] = clock64();
                         float wo[TDE_MAX_OUT];
                         if (last) {
 #pragma unroll
-                            for (int o = 0; o < TDE_MAX_OUT; ++o) wo[o] = o < p.n_out ? wout_s[o * W + n] : 0.0f;
+                            for (int o = 0; o < TDE_MAX_OUT; ++o) wo[o] = wo_v[v][o];
                         }
                         uint32_t taddr = 0;
                         if (!last) {
@@ -364,6 +393,7 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_backward_tc_kernel(
 #pragma unroll
                             for (int i = 0; i < TDE_MAX_IN; ++i)
                                 if (i < p.d_in) slab_add(gp_lo + (size_t)n * p.d_in + i, dw_in[i], first);
+                            if (stamp) dst[3] = clock64();
                         }
                         if (last) {
 #pragma unroll
@@ -375,6 +405,9 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_backward_tc_kernel(
                 };
                 layer_body(std::integral_constant<int, 2>{}, p.L - 1);
                 if (tstamp) p.dbg_buf[45] = clock64();      // last hidden layer's adjoint (from the seeds) published
+                // fetch the next tile's points and seeds now: the MMAs of the first layer have just started, this warp would
+                // otherwise wait for them
+                if (has_next && p.stage_dbuf) stage_tile(next_tile, xs_buf + (cur ^ 1) * stage_floats);
                 for (int l = p.L - 2; l >= 1; --l) {
                     layer_body(std::integral_constant<int, 1>{}, l);
                     if (tstamp && l <= 2) p.dbg_buf[45 + l] = clock64();     // [46]: layer 1 done, [47]: layer 2 done
@@ -386,7 +419,14 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_backward_tc_kernel(
                     for (int pt = 0; pt < PTS; ++pt) s += seeds_s[(pt * J) * 4 + et];   // channel 0, output et
                     slab_add(gp + p.gp_off_b_out + et, s, first);
                 }
-                epi_sync();   // xs / seeds_s are rewritten by the next tile
+                if (has_next) load_stash(p.L - 1, row_of(next_tile));     // in flight across the barrier
+                epi_sync();   // the next tile's staging is visible to every warp; this tile's buffer may be refilled
+                if (p.stage_dbuf) {
+                    cur ^= 1;
+                } else if (has_next) {      // one buffer only: refill it now
+                    stage_tile(next_tile, xs_buf);
+                    epi_sync();
+                }
                 if (tstamp) p.dbg_buf[44] = clock64();      // tile done
             }
         }

@@ -10,7 +10,7 @@
 // D         = TMEM, lane = neuron => after tcgen05.ld every epilogue thread owns ALL jet channels of its neuron for its
 //             points of the tile, which is exactly what the jet activation needs (no cross-lane exchange).
 // Roles: warp 0 weight producer, warp 1 MMA issuer (one elected thread), warps 4.. epilogue (8 warps per 128-neuron block:
-// one thread per neuron and half of the tile's points).  Shared memory: [planes][weight stages][w_out][x][y][barriers].
+// one thread per neuron and half of the tile's points).  Shared memory: [planes][weight stages][x][y][barriers].
 #pragma once
 #include <type_traits>
 #include <utility>
@@ -113,6 +113,21 @@ __device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
             smem_u32(dst_smem)),
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// same copy with an L2 evict-last policy: the weight images (a few MB, re-read by every CTA for every tile) must stay in L2
+// next to tens of GB of streamed stash / Hbar traffic
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_mc_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t cta_mask,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, [%3], %4, %5;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -463,8 +478,9 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_forward_tc_kernel(c
     constexpr uint32_t z_planes = (uint32_t)(W / 32) * P::kAtom;
     constexpr uint32_t chunk_bytes = (uint32_t)KSC * 8192u;         // one neuron block, KSC k-steps: [hi|lo][kgroup 2][16 row groups][8][4] floats
     unsigned char* wst = zpl + z_planes;                             // [n_stages][chunk_bytes]
-    float* wout_s = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);   // [n_out][W]
-    float* xs = wout_s + p.n_out * W;            // [PTS][d_in]
+    // (w_out, 3 KB for three outputs, is read through L1 where it is needed: those 3 KB are the difference between three
+    // and four 16 KB weight stages at W = 256, J = 5, and the MMA phase runs at the rate the stages in flight allow)
+    float* xs = reinterpret_cast<float*>(wst + (size_t)n_stages * chunk_bytes);            // [PTS][d_in]
     float* ybuf = xs + PTS * p.d_in;             // [J*n_out][PTS]
     float* bout_s = ybuf + J * TDE_MAX_OUT * PTS; // [4]
     // barriers at the tail (kTcTailBytes): the planes need the 1024 B alignment of the base, a header would waste ~850 B
@@ -515,12 +531,18 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_forward_tc_kernel(c
             int s = 0;
             uint32_t ph = 0;
             const uint32_t part = chunk_bytes / kTcCluster;
+            const uint64_t pol = l2_policy_evict_last();
+            const bool hint = !(p.dbg & 16);
             for (int64_t pair = first_pair; pair < n_pairs; pair += pair_step) {
                 for (int l = 1; l < p.L; ++l) {
                     const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wc) + (size_t)(l - 1) * n_chunks * chunk_bytes;
                     for (int ks = 0; ks < n_chunks; ++ks) {
                         mbar_wait(&empty[s], ph ^ 1);   // both CTAs have finished reading this stage
                         mbar_expect_tx(&full[s], chunk_bytes);      // my part + the peer's part will land here
+                        if (hint)
+                            bulk_g2s_mc_hint(wst + (size_t)s * chunk_bytes + crank * part, src + (size_t)ks * chunk_bytes + crank * part, part,
+                                             &full[s], (uint16_t)((1u << kTcCluster) - 1), pol);
+                        else
                         bulk_g2s_mc(wst + (size_t)s * chunk_bytes + crank * part, src + (size_t)ks * chunk_bytes + crank * part, part,
                                     &full[s], (uint16_t)((1u << kTcCluster) - 1));
                         if (++s == n_stages) {
@@ -570,7 +592,6 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_forward_tc_kernel(c
             const int et = e * 32 + lane;            // 0..n_epi-1 dense index for strided loops
             auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory"); };
 
-            for (int i = et; i < p.n_out * W; i += n_epi) wout_s[i] = p.w_out[i];
             if (et < p.n_out) bout_s[et] = p.b_out[et];
             // byte offset of element (col, k = n) inside a Z plane.  The k-atom parity (where the hi part sits), the byte inside the
             // 16 B chunk and the chunk index depend on the lane quarter and the lane only: a visit of block v adds 4 v k-atoms.
@@ -718,39 +739,47 @@ __global__ void __launch_bounds__(tc_threads(W, PTS), 1) jet_forward_tc_kernel(c
                 epi_sync();   // every neuron's last-layer z is in the planes
                 if (tstamp) p.dbg_buf[42] = clock64();      // last layer's epilogue done everywhere
 
-                // ---- output layer, z = hi + lo: a warp takes 8 jet columns, its four 8-lane groups split the K = W reduction.
-                // 8 lanes reading the same 16 B k-chunk of 8 different columns hit 8 different bank groups (that is what the
-                // 128 B swizzle is for); the first version (4 consecutive lanes per column) was 4-way bank-conflicted: 5 k of the
-                // 8 k cycles this step took with the tensor pipe idle.
-                for (int cw = e; cw < N / 8; cw += n_epi_warps) {       // whole warps: the shuffles below need all 32 lanes
-                    const int col = cw * 8 + (lane & 7), part = lane >> 3;
-                    float y[TDE_MAX_OUT];
+                // ---- output layer, z = hi + lo.  A warp takes whole jet columns; its 32 lanes split the K = W reduction by 16 B
+                // k-chunks (lane, lane + 32, ...), so a lane's rows of w_out are a handful of registers loaded once per tile and
+                // the plane reads of a warp are four full 128 B rows per instruction (conflict-free).  w_out itself is read from
+                // global memory (L1): shared memory has no room for it next to a fourth weight stage, and an inner loop that
+                // fetched it per k-chunk doubled the time of this step (tensor pipe idle).
+                {
+                    constexpr int KPL = W / 128;         // k-chunks per lane
+                    float4 wv[TDE_MAX_OUT][KPL];
 #pragma unroll
-                    for (int o = 0; o < TDE_MAX_OUT; ++o) y[o] = 0.0f;
-                    const uint32_t cbase = (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u;
-                    for (int kg = part; kg < W / 4; kg += 4) {
-                        const uint32_t ho = P::template hi_off<kAccSets>((uint32_t)kg >> 3);
-                        const uint32_t o4 = (uint32_t)(kg >> 3) * P::kAtom + cbase + ((((uint32_t)kg & 7u) ^ (uint32_t)(col & 7)) << 4);
-                        const float4 a = *reinterpret_cast<const float4*>(zpl + o4 + ho);
-                        const float4 b = *reinterpret_cast<const float4*>(zpl + o4 + (P::kHalf - ho));
-                        const float zz[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+                    for (int o = 0; o < TDE_MAX_OUT; ++o)
+#pragma unroll
+                        for (int j = 0; j < KPL; ++j)
+                            wv[o][j] = o < p.n_out ? __ldg(reinterpret_cast<const float4*>(p.w_out + o * W + (lane + 32 * j) * 4))
+                                                   : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    for (int col = e; col < N; col += n_epi_warps) {       // whole warps: the shuffles below need all 32 lanes
+                        float y[TDE_MAX_OUT];
+#pragma unroll
+                        for (int o = 0; o < TDE_MAX_OUT; ++o) y[o] = 0.0f;
+                        const uint32_t cbase = (uint32_t)(col >> 3) * 1024u + (uint32_t)(col & 7) * 128u;
+#pragma unroll
+                        for (int j = 0; j < KPL; ++j) {
+                            const uint32_t kg = (uint32_t)(lane + 32 * j);
+                            const uint32_t ho = P::template hi_off<kAccSets>(kg >> 3);
+                            const uint32_t o4 = (kg >> 3) * P::kAtom + cbase + (((kg & 7u) ^ (uint32_t)(col & 7)) << 4);
+                            const float4 a = *reinterpret_cast<const float4*>(zpl + o4 + ho);
+                            const float4 b = *reinterpret_cast<const float4*>(zpl + o4 + (P::kHalf - ho));
+                            const float zz[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+#pragma unroll
+                            for (int o = 0; o < TDE_MAX_OUT; ++o)
+                                y[o] = fmaf(zz[0], wv[o][j].x, fmaf(zz[1], wv[o][j].y, fmaf(zz[2], wv[o][j].z, fmaf(zz[3], wv[o][j].w, y[o]))));
+                        }
 #pragma unroll
                         for (int o = 0; o < TDE_MAX_OUT; ++o)
-                            if (o < p.n_out) {
-                                const float4 w4 = *reinterpret_cast<const float4*>(wout_s + o * W + kg * 4);
-                                y[o] = fmaf(zz[0], w4.x, fmaf(zz[1], w4.y, fmaf(zz[2], w4.z, fmaf(zz[3], w4.w, y[o]))));
-                            }
-                    }
 #pragma unroll
-                    for (int o = 0; o < TDE_MAX_OUT; ++o) {
-                        y[o] += __shfl_xor_sync(0xffffffffu, y[o], 8);
-                        y[o] += __shfl_xor_sync(0xffffffffu, y[o], 16);
-                    }
-                    if (part == 0) {
-                        const int pt = col / J, c = col - pt * J;
+                            for (int sh = 16; sh > 0; sh >>= 1) y[o] += __shfl_xor_sync(0xffffffffu, y[o], sh);
+                        if (lane == 0) {
+                            const int pt = col / J, c = col - pt * J;
 #pragma unroll
-                        for (int o = 0; o < TDE_MAX_OUT; ++o)
-                            if (o < p.n_out) ybuf[(c * p.n_out + o) * PTS + pt] = y[o] + (c == 0 ? bout_s[o] : 0.0f);
+                            for (int o = 0; o < TDE_MAX_OUT; ++o)
+                                if (o < p.n_out) ybuf[(c * p.n_out + o) * PTS + pt] = y[o] + (c == 0 ? bout_s[o] : 0.0f);
+                        }
                     }
                 }
                 epi_sync();

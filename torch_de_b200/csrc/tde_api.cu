@@ -149,6 +149,7 @@ struct Geometry {
     // tcgen05 forward (wide layers)
     int use_tc, use_pair, tc_mb, tc_stages, tc_smem, tc_nacc;
     int tc_pts, tc_ksc;          // points per tensor-core tile (16; 8 for W = 512), k-steps per weight chunk
+    int tc_dbuf;                 // reverse sweep: second (x | seeds) staging buffer fits
     int use_tc_bwd, dw_smem;
     int dw_w, dw_split;          // weight-gradient GEMM: block edge one CTA accumulates (<= 256), halves per dimension (W = 512: 2)
     int64_t o_wct, o_hbar, grid_b1, grid_b2;
@@ -310,10 +311,18 @@ int make_geometry(const TdeNet* net, const TdeJetSpec* spec, int64_t B, Geometry
         if (shape_ok && L >= 2 && (g.W > 256 || g.TP % g.tc_pts == 0) && !no_tc) {
             const int64_t atomk = (Ntc / 8) * 1024;
             const int pts = g.use_pair ? 2 * tde::kTcPoints : g.tc_pts;     // points staged per CTA (x, seeds)
-            // [planes][weight stages][w_out][x][seeds | y, 4 (padded) outputs per channel][tail: barriers]; the pair kernels keep a 1 KB header
-            const int64_t fixed = (g.use_pair ? 1024 : tde::kTcTailBytes) + 2 * (g.W / 32) * atomk +
-                                  4 * ((int64_t)g.n_out * g.W + pts * g.d_in + (int64_t)g.J * 4 * pts);
+            // [planes][weight stages][w_out][2 x (x | seeds or y, 4 (padded) outputs per channel)][tail: barriers]; the reverse sweep
+            // stages the next tile's x / seeds while the current one runs; the pair kernels keep a 1 KB header
+            const int64_t staging = 4 * (pts * g.d_in + (int64_t)g.J * 4 * pts);
+            // (the pair kernels also keep w_out in shared memory)
+            int64_t fixed = (g.use_pair ? 1024 + 4 * ((int64_t)g.n_out * g.W) : tde::kTcTailBytes) + 2 * (g.W / 32) * atomk + staging;
             const int64_t chunk = g.use_pair ? tde::kPairChunkBytes : (int64_t)g.tc_ksc * 8192;
+            // the second staging buffer is taken only when it does not cost a weight stage
+            g.tc_dbuf = 0;
+            if (!g.use_pair && (kSmemLimit - fixed - staging) / chunk == (kSmemLimit - fixed) / chunk && (kSmemLimit - fixed - staging) / chunk >= 2) {
+                g.tc_dbuf = 1;
+                fixed += staging;
+            }
             for (int st = tde::kTcMaxStages; st >= 2; --st)
                 if (fixed + st * chunk <= kSmemLimit) {
                     if (options().tc_stages > 0) st = std::max(2, std::min(st, options().tc_stages));   // experiments only
@@ -968,6 +977,8 @@ static int backward_core(const TdeNet* net, const TdeJetSpec* spec, const Geomet
         for (int a = 0; a < TDE_MAX_FIRST; ++a) t.first_in[a] = a < spec->n_first ? spec->first_in[a] : 0;
         t.wct = ws + g.o_wct; t.w_out = ws + g.o_wo;
         t.seeds = seeds; t.ld_seeds = ld_seeds; t.stash = stash;
+        t.stage_dbuf = g.tc_dbuf;
+        t.dbg = options().tc_dbg;
         t.hbar = ws + g.o_hbar;
         t.stash_layer_stride = g.stash_layer_stride;
         t.tiles_per_bw_tile = g.TP / tde::kTcPoints;
@@ -982,7 +993,7 @@ static int backward_core(const TdeNet* net, const TdeJetSpec* spec, const Geomet
         d.gpart = t.gpart; d.gp_stride = g.gp_stride; d.gp_off_hidden = g.g_hidden;
         static long long* bdbg = nullptr;
         if (options().tc_dbg & 4) {
-            if (!bdbg) { cudaMalloc(&bdbg, 64 * sizeof(long long)); cudaMemset(bdbg, 0, 64 * sizeof(long long)); }
+            if (!bdbg) { cudaMalloc(&bdbg, 80 * sizeof(long long)); cudaMemset(bdbg, 0, 80 * sizeof(long long)); }
             t.dbg_buf = bdbg;
         }
         {
@@ -990,7 +1001,7 @@ static int backward_core(const TdeNet* net, const TdeJetSpec* spec, const Geomet
             TDE_CUDA(g.disp->bwd_tc(t, (int)g.grid_b1, g.tc_smem, st));
         }
         if (t.dbg_buf) {
-            long long h[64];
+            long long h[80];
             cudaStreamSynchronize(st);
             cudaMemcpy(h, bdbg, sizeof h, cudaMemcpyDeviceToHost);
             for (int l = 0; l < 3; ++l)
@@ -998,6 +1009,12 @@ static int backward_core(const TdeNet* net, const TdeJetSpec* spec, const Geomet
                     const long long* d = h + 16 + (l * 2 + b) * 4;
                     fprintf(stderr, "[tc dbg] bwd layer %d block %d: start %lld  acc_ready %lld  body_end %lld  published %lld\n", 5 - l, b,
                             d[0] - h[16], d[1] - h[16], d[2] - h[16], d[3] - h[16]);
+                }
+            for (int k = 0; k < 2; ++k)
+                for (int b = 0; b < 2; ++b) {
+                    const long long* d = h + (k ? 58 : 50) + b * 4;
+                    fprintf(stderr, "[tc dbg] bwd %s block %d: start %lld  acc_ready %lld  body_end %lld  published %lld (from tile start)\n",
+                            k ? "input layer" : "last hidden layer", b, d[0] - h[40], d[1] - h[40], d[2] - h[40], d[3] - h[40]);
                 }
             fprintf(stderr, "[tc dbg] bwd tile: inputs staged %lld  last-layer adjoint %lld  layer-5 start %lld | layer 2 done %lld  layer 1 done %lld  input layer done %lld  tile done %lld\n",
                     h[41] - h[40], h[45] - h[40], h[16] - h[40], h[47] - h[40], h[46] - h[40], h[48] - h[40], h[44] - h[40]);
