@@ -252,23 +252,34 @@ def run_ours(args, rank, local_rank, world):
     net = wl.make_net().to(dev)
     pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
     runner = pinn.deriv_method._full
-    host_groups = {g: x.pin_memory() for g, x in wl.sample(n_col, n_bnd, seed=1234 + rank).items()}
-    dev_groups = {g: x.to(dev) for g, x in host_groups.items()}
-    batch = T.make_batch(wl.input_vars, dev_groups)
-    losses = wl.build_losses(list(dev_groups.keys()))
+    state = {}
+
+    def make_shard(n_col_rank, res_scale):
+        state["host"] = {g: x.pin_memory() for g, x in wl.sample(n_col_rank, n_bnd, seed=1234 + rank).items()}
+        state["dev"] = {g: x.to(dev) for g, x in state["host"].items()}
+        state["batch"] = T.make_batch(wl.input_vars, state["dev"])
+        state["res_scale"] = res_scale          # weight of this rank's residual rows (1 with equal shards)
+        state["n_col"] = n_col_rank
+    make_shard(n_col, 1.0)
+    losses = wl.build_losses(list(state["dev"].keys()))
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)        # Lid_Driven_Cavity.py:71
     flat = FlatGrads(net)
-    n_pts_rank = sum(x.shape[0] for x in dev_groups.values())
 
-    ar_events = []          # (before, after) CUDA events around the gradient all-reduce of every timed step
+    ar_events = []          # (step start, before, after) CUDA events around the gradient all-reduce of every timed step
 
     def step(from_host=False, record_ar=False):
+        if record_ar and world > 1:
+            es = torch.cuda.Event(enable_timing=True)
+            es.record()
         if from_host:
-            for g, x in host_groups.items():
-                dev_groups[g].copy_(x, non_blocking=True)
-        out = pinn.calculate(batch)
-        loss = losses(batch, out)
-        total = wl.combine(loss.grouped_losses("loss_type"))
+            for g, x in state["host"].items():
+                state["dev"][g].copy_(x, non_blocking=True)
+        out = pinn.calculate(state["batch"])
+        loss = losses(state["batch"], out)
+        by_type = loss.grouped_losses("loss_type")
+        if state["res_scale"] != 1.0:            # unequal shards: the residual mean of this rank weighs n_rank / N, not 1 / world
+            by_type["residual"] = by_type["residual"] * state["res_scale"]
+        total = wl.combine(by_type)
         total.backward()
         if world > 1:
             if record_ar:
@@ -276,7 +287,7 @@ def run_ours(args, rank, local_rank, world):
                 ea.record()
                 flat.all_reduce_mean()
                 eb.record()
-                ar_events.append((ea, eb))
+                ar_events.append((es, ea, eb))
             else:
                 flat.all_reduce_mean()
         opt.step()
@@ -306,6 +317,8 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
+    shards = [n_col] * world
+    n_pts_rank = sum(x.shape[0] for x in state["dev"].values())
     step()              # settle: one more untimed step after the first full synchronisation (allocator / clocks steady)
     barrier()
 
@@ -327,22 +340,29 @@ def run_ours(args, rank, local_rank, world):
         m, n = C.c_double(), C.c_int32()
         lib.tde_profile_kind(k, C.byref(m), C.byref(n))
         ksum += m.value
-    ar_ms = sum(a.elapsed_time(b) for a, b in ar_events)
+    ar_ms = sum(a.elapsed_time(b) for _, a, b in ar_events)
     mine = torch.tensor([ksum / args.steps, ar_ms / args.steps], device=dev, dtype=torch.float64)
     per_rank = [torch.zeros_like(mine) for _ in range(world)]
+    # per step: this rank's compute time (step start -> gradient ready).  The step ends for everybody when the slowest rank of
+    # THAT step is ready, so mean over steps of (max over ranks - mean over ranks) is what synchronous DP pays for rank skew
+    # and step-to-step jitter together
+    compute = torch.tensor([s0.elapsed_time(a) for s0, a, _ in ar_events] or [0.0], device=dev, dtype=torch.float64)
+    all_compute = [torch.zeros_like(compute) for _ in range(world)]
     if world > 1:
         dist.all_gather(per_rank, mine)
+        dist.all_gather(all_compute, compute)
     else:
-        per_rank = [mine]
+        per_rank, all_compute = [mine], [compute]
     per_rank = torch.stack(per_rank).cpu()
+    all_compute = torch.stack(all_compute).cpu()            # [ranks, steps]
 
     graphed_ms = None
     if args.graphed and world == 1:
         gopt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
 
         def graph_body():
-            out = pinn.calculate(batch)
-            total = wl.combine(losses(batch, out).grouped_losses("loss_type"))
+            out = pinn.calculate(state["batch"])
+            total = wl.combine(losses(state["batch"], out).grouped_losses("loss_type"))
             total.backward()
             gopt.step()
             flat.zero()
@@ -361,7 +381,7 @@ def run_ours(args, rank, local_rank, world):
 
     if rank != 0:
         return
-    n_pts_job = n_pts_rank * world
+    n_pts_job = sum(shards) + world * (n_pts_rank - shards[rank])      # every rank holds boundary groups of the same size
     value = n_pts_job * args.steps / (ms_total * 1e-3)
     e2e_value = n_pts_job * args.steps / (ms_e2e * 1e-3)
 
@@ -440,7 +460,7 @@ def run_ours(args, rank, local_rank, world):
 
     reference_gpu = None
     if world == 1 and not args.no_cpu_baseline:
-        del batch, dev_groups
+        state.pop("batch"), state.pop("dev")
         torch.cuda.empty_cache()
         try:
             best, sweep = gpu_reference_best(args.workload, dev)
@@ -451,7 +471,7 @@ def run_ours(args, rank, local_rank, world):
         except Exception as exc:  # noqa: BLE001 - informational leg only
             reference_gpu = {"unavailable": repr(exc)[:200]}
 
-    h2d = sum(x.numel() * 4 for x in host_groups.values())
+    h2d = sum(x.numel() * 4 for x in state["host"].values())
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -471,7 +491,11 @@ def run_ours(args, rank, local_rank, world):
                                                  "max": float(per_rank[:, 0].max())},
                       "allreduce_ms_per_step": {"min": float(per_rank[:, 1].min()), "median": float(per_rank[:, 1].median()),
                                                 "max": float(per_rank[:, 1].max())},
-                      "note": "all-reduce time = wait for the slowest rank + the collective, from CUDA events around it"}}
+                      "compute_ms_per_step": {"mean_over_ranks": float(all_compute.mean()),
+                                              "mean_of_per_step_max": float(all_compute.max(dim=0).values.mean()),
+                                              "slowest_rank_mean": float(all_compute.mean(dim=1).max())},
+                      "note": "all-reduce time = wait for the slowest rank of the step + the collective (21-28 us alone, "
+                              "tools/allreduce_probe.py), from CUDA events around it; compute = step start -> gradient ready"}}
     if graphed_ms is not None:
         line["graphed"] = {"ms_per_step": graphed_ms, "value": n_pts_job / (graphed_ms * 1e-3), "unit": UNIT,
                            "note": "same step replayed as one CUDA graph (torch_de_b200.GraphedStep); `value` above is the eager public API"}

@@ -38,3 +38,14 @@ def test_flat_gradient_allreduce_equals_global_mean():
     net(x_all).pow(2).mean().backward()       # global mean
     ref = torch.cat([p.grad.flatten() for p in net.parameters()])
     assert torch.allclose(ret['flat'], ref, rtol=1e-5, atol=1e-7)
+
+
+def test_proportional_shards_equalise_the_step_time():
+    from torch_de_b200.dp import proportional_shards
+    sizes = [500_000] * 4
+    ms = [40.0, 41.0, 42.0, 40.5]                       # rank 2 is the slowest
+    new = proportional_shards(ms, sizes)
+    assert sum(new) == sum(sizes) and all(n % 32 == 0 for n in new[:0] + new[1:])     # (the remainder lands on the fastest rank)
+    t_new = [n / (s / t) for n, s, t in zip(new, sizes, ms)]
+    assert max(t_new) - min(t_new) < 0.01 and max(t_new) < max(ms)
+    assert new[2] < new[1] < new[3] < new[0]
