@@ -358,6 +358,9 @@ def run_ours(args, rank, local_rank, world):
 
     graphed_ms = None
     if args.graphed and world == 1:
+        import gc
+        gc.collect()            # no autograd graph of an eager step may be alive when the capture starts (its AccumulateGrad
+        torch.cuda.synchronize(dev)         # nodes belong to the default stream)
         gopt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
 
         def graph_body():

@@ -523,3 +523,36 @@ def test_graphed_step_replays_the_eager_step_bitwise():
         results[mode] = (losses, torch.cat([p.detach().flatten().cpu() for p in net.parameters()]))
     assert results['eager'][0] == results['graph'][0]
     assert torch.equal(results['eager'][1], results['graph'][1])
+
+
+def test_no_reference_cycle_keeps_the_stash_alive():
+    """A training step must free its stream block and activation stash by reference counting alone (the cycle collector runs
+    whenever it likes: at LDC scale a leaked step is 21 GB)."""
+    import gc
+    z, owl, params, groups = load('ldc_small')
+    wl = product_workload('ldc_small')
+    net, lins = load_net(wl, params, 'cuda')
+    pinn = T.DE_Getter(net, wl.input_vars, wl.output_vars, wl.derivatives)
+    batch = T.make_batch(wl.input_vars, {g: x.cuda() for g, x in groups.items()})
+    handler = wl.build_losses(list(groups.keys()))
+
+    def step():
+        out = pinn.calculate(batch)
+        loss = handler(batch, out)
+        loss.point_error()                      # materialises the per-point pass too
+        total = wl.combine(loss.grouped_losses('loss_type'))
+        total.backward()
+        return float(total)
+
+    gc.collect()
+    gc.disable()
+    try:
+        step()
+        torch.cuda.synchronize()
+        base = torch.cuda.memory_allocated()
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        assert torch.cuda.memory_allocated() <= base + (1 << 16), (torch.cuda.memory_allocated(), base)
+    finally:
+        gc.enable()

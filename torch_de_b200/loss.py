@@ -45,9 +45,9 @@ class Loss:
         the row's whole group (tde_residual_loss_points) and fills residual + weighting of every row of that group.  These
         are detached values for samplers and diagnostics (R3_sampler, Causal_weighting), as in sampling.py:89 `no_grad`."""
         if row.get('residual') is None and row.get('_points') is not None:
-            res, wts, rows_of_group = row['_points']()
-            for i, r in enumerate(rows_of_group):
-                r['residual'], r['weighting'] = res[i], wts[i]
+            run, i = row['_points']          # (point pass of the row's group -- shared by its rows --, row index in the group)
+            res, wts = run()
+            row['residual'], row['weighting'] = res[i], wts[i]
 
     def point_error(self) -> List[Tensor]:
         for row in self.losses:
@@ -160,7 +160,7 @@ class Loss_handler:
         ranges = getattr(batched_output, 'ranges', None) or {}
         n_all = block.shape[1] if block is not None else 0
         rows = []
-        group_rows: Dict[str, list] = {}
+        group_rows: Dict[str, list] = {}      # group -> [point pass, rows handed out so far]
         for spec in self.rows:
             src = None if block is None else (block, (0, n_all) if spec['custom'] else ranges.get(spec['group']))
             if src is not None and src[1] is None:
@@ -171,9 +171,11 @@ class Loss_handler:
                 row['residual'] = None
                 row['weighting'] = None
                 row['aggregated_loss'] = fused_groups[spec['group']].pop(0)
-                mine = group_rows.setdefault(spec['group'], [])
-                mine.append(row)
-                row['_points'] = self._point_pass(block, self._launched[spec['group']], mine)
+                g = spec['group']
+                if g not in group_rows:
+                    group_rows[g] = [self._point_pass(block, self._launched[g]), 0]
+                row['_points'] = (group_rows[g][0], group_rows[g][1])
+                group_rows[g][1] += 1
                 rows.append(row)
                 continue
             row = dict(spec)
@@ -192,8 +194,10 @@ class Loss_handler:
         return Loss(rows, aggregation_method, power)
 
     @staticmethod
-    def _point_pass(block, launch, rows_of_group):
-        """Closure that runs the loss kernel's point pass for one fused group once and caches the result."""
+    def _point_pass(block, launch):
+        """Closure that runs the loss kernel's point pass for one fused group once and caches the result.  It must not refer
+        back to the rows that hold it: a reference cycle would keep the stream block -- and through it the activation stash of
+        the step, tens of GB -- alive until Python's cycle collector happens to run."""
         cache = []
 
         def run():
@@ -201,7 +205,7 @@ class Loss_handler:
                 gp, aux, lo, n = launch
                 with torch.no_grad():
                     cache.append(FL.point_rows(block.detach(), gp, aux, lo, n))
-            return cache[0][0], cache[0][1], rows_of_group
+            return cache[0]
         return run
 
     # -- fused path ---------------------------------------------------------------------------
