@@ -24,6 +24,15 @@ def _worker(rank, world, port, ret):
         ret['flat'] = flat.flat.clone()
     flat.zero()
     assert all(float(p.grad.abs().sum()) == 0.0 for p in net.parameters())
+    # a caller that resets the gradients to None (optimizer.zero_grad() default) must not end up reducing a stale buffer
+    for p in net.parameters():
+        p.grad = None
+    net(x).pow(2).mean().backward()
+    assert not flat.check_aliasing()
+    flat.all_reduce_mean()
+    assert flat.check_aliasing()
+    if rank == 0:
+        ret['flat_after_reset'] = flat.flat.clone()
     dist.destroy_process_group()
 
 
@@ -38,6 +47,7 @@ def test_flat_gradient_allreduce_equals_global_mean():
     net(x_all).pow(2).mean().backward()       # global mean
     ref = torch.cat([p.grad.flatten() for p in net.parameters()])
     assert torch.allclose(ret['flat'], ref, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(ret['flat_after_reset'], ref, rtol=1e-5, atol=1e-7)
 
 
 def test_proportional_shards_equalise_the_step_time():

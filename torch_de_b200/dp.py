@@ -23,12 +23,29 @@ class FlatGrads:
             o += p.numel()
 
     def zero(self):
+        """Use this instead of `optimizer.zero_grad()`: the default `set_to_none=True` drops the views, autograd then
+        allocates fresh gradients and the flat buffer is no longer what the parameters accumulate into."""
         self.flat.zero_()
+
+    def _rebind(self):
+        """Re-install the views (after an `optimizer.zero_grad(set_to_none=True)` by the caller), keeping whatever gradients
+        the parameters hold at the moment."""
+        o = 0
+        for p in self.params:
+            view = self.flat[o:o + p.numel()].view_as(p)
+            if p.grad is None:
+                view.zero_()
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            p.grad = view
+            o += p.numel()
 
     def all_reduce_mean(self, group=None):
         """Sum over ranks, divide by world size: with equal shards the mean of local means is the global mean
         (loss.py:26,57 `mean` over the global point count)."""
         world = dist.get_world_size(group)
+        if not self.check_aliasing():       # somebody reset the gradients to None: reducing a stale buffer would go unnoticed
+            self._rebind()
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         if world > 1:
             self.flat.mul_(1.0 / world)
@@ -44,8 +61,9 @@ class FlatGrads:
 
 
 def shard(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
-    """Contiguous 1/world slice of a point set (equal sizes; the tail remainder is dropped like the reference's
-    sampler drops a ragged last batch, utils/data.py:233-243)."""
+    """Contiguous 1/world slice of a point set.  Shards are EQUAL (the mean of the ranks' means is then the global mean): the
+    `x.shape[0] % world` points at the tail are dropped, like the reference's sampler drops a ragged last batch
+    (utils/data.py:233-243)."""
     n = x.shape[0] // world
     return x[rank * n:(rank + 1) * n]
 
