@@ -128,3 +128,34 @@ def test_engine_has_no_cpu_path():
     pinn = T.DE_Getter(T.MLP(2, 1, 64, 2), ['x', 't'], ['u'], ['u_x'])
     with pytest.raises(RuntimeError, match='CUDA'):
         pinn.calculate(torch.rand(4, 2))
+
+
+def test_abi_argument_checks_of_the_round_two_entry_points():
+    """tde_jet_backward_range / tde_residual_loss_points / GRID2D programs: bad arguments come back as error codes with a
+    message, before anything is launched (so these run without a device)."""
+    lib = _lib.lib()
+    r = _runner(2, 1, 64, 3, ['u_x'], ['x', 't'], ['u'])
+    r.plan(100)
+    one = C.c_void_p(16)          # any non-null pointer: the checks below fail before it is touched
+    for lo, hi in ((-1, 10), (50, 40), (0, 101)):
+        rc = lib.tde_jet_backward_range(C.byref(r._net), C.byref(r._spec), one, 100, one, one, 100, lo, hi, 1.0, one, one, None)
+        assert rc != 0 and b'range' in lib.tde_last_error()
+    assert lib.tde_jet_backward_range(C.byref(r._net), C.byref(r._spec), one, 100, one, one, 100, 32, 32, 1.0, one, one, None) == 0   # empty range
+    prog = _lib.TdeLossProgram()
+    prog.n_ops, prog.n_rows = 1, 1
+    prog.ops[0].op, prog.ops[0].dst, prog.ops[0].a = _lib.OP_LOAD, 0, 0
+    prog.res_reg[0], prog.w_aux[0], prog.w_reg[0] = 0, -1, -1
+    assert lib.tde_residual_loss_points(C.byref(prog), one, 8, 1, None, 0, 0, 8, None, None, None) != 0
+    assert b'nothing to compute' in lib.tde_last_error()
+    prog.n_ops = 2
+    prog.ops[1].op, prog.ops[1].dst, prog.ops[1].a, prog.ops[1].b, prog.ops[1].imm = _lib.OP_GRID2D, 1, 0, 0, 0.0
+    assert lib.tde_residual_loss_points(C.byref(prog), one, 8, 1, None, 0, 0, 8, one, None, None) != 0
+    assert b'grid 0 out of range' in lib.tde_last_error()         # the program names a grid it does not carry
+    prog.n_grids = 1
+    assert lib.tde_residual_loss_points(C.byref(prog), one, 8, 1, None, 0, 0, 8, one, None, None) != 0
+    assert b'null pointer or empty axis' in lib.tde_last_error()
+    prog.n_grids = 0
+    prog.n_ops = 1
+    prog.w_reg[0] = _lib.MAX_REGS
+    assert lib.tde_residual_loss_points(C.byref(prog), one, 8, 1, None, 0, 0, 8, one, None, None) != 0
+    assert b'weight register' in lib.tde_last_error()
