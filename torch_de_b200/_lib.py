@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtde_jet.so")
+# (TDE_LIB_PATH: load another build of the same library -- A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("TDE_LIB_PATH") or os.path.join(_HERE, "csrc", "libtde_jet.so")
 
 ACT_NONE, ACT_TANH, ACT_SIN = 0, 1, 2
 ACT_FOURIER = 0x100
