@@ -160,7 +160,7 @@ def gpu_reference_steps(workload, n_col, n_bnd, steps, warmup, dev):
     return n_pts * steps / (e0.elapsed_time(e1) * 1e-3), n_pts, kind
 
 
-def gpu_reference_best(workload, dev, sizes=(4096, 16384, 65536, 131072)):
+def gpu_reference_best(workload, dev, sizes=(4096, 16384, 65536, 131072, 262144)):
     """Sweep the micro-batch and keep the reference's best throughput (it is given its best shot); a size that does not fit
     (the reference keeps ~0.5 MB of autograd state per LDC point) ends the sweep."""
     sweep, best = [], None
