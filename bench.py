@@ -167,8 +167,10 @@ def gpu_reference_best(workload, dev, sizes=(4096, 16384, 65536, 131072, 262144)
     for n_col in sizes:
         try:
             v, npts, kind = gpu_reference_steps(workload, n_col, max(1, n_col // 64), 3, 2, dev)
-        except torch.OutOfMemoryError:
-            sweep.append({"points": n_col, "value": None, "note": "out of memory"})
+        except (torch.OutOfMemoryError, RuntimeError) as exc:
+            if best is None:
+                raise
+            sweep.append({"points": n_col, "value": None, "note": "out of memory" if isinstance(exc, torch.OutOfMemoryError) else repr(exc)[:80]})
             torch.cuda.empty_cache()
             break
         sweep.append({"points": npts, "value": v})
