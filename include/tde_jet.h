@@ -100,7 +100,8 @@ int tde_plan(const TdeNet* net, const TdeJetSpec* spec, int64_t n_points, TdePla
 /*
  * Forward jets.  x[n_points][d_in] row-major.  out[(c*n_out + o)*ld_out + p] = channel c of output o at
  * point p (SoA: one contiguous stream per (channel, output)).  stash may be NULL (inference / value-only
- * groups: nothing is kept for a backward).  workspace must hold plan.workspace_bytes.
+ * groups: nothing is kept for a backward).  workspace must hold plan.workspace_bytes; workspace, stash and the stream
+ * blocks must be 16-byte aligned (vector and bulk-copy accesses; any cudaMalloc / torch allocation is).
  */
 int tde_jet_forward(const TdeNet* net, const TdeJetSpec* spec, const float* x, int64_t n_points,
                     float* out, int64_t ld_out, float* stash, void* workspace, void* stream);
