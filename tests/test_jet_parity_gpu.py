@@ -468,6 +468,11 @@ def test_gradnorm_weights_follow_reference_rule(fixture):
     # a plain tensor that does not come from the loss table takes the k-pass rule
     T.GradNorm(net, w0[:1], rows.sum())
     assert T.GradNorm.last_path == 'k-pass'
+    # like autograd's saved-tensor check: a forward whose weights were changed in place afterwards cannot be swept again
+    with torch.no_grad():
+        next(net.parameters()).add_(0.0)
+    with pytest.raises(RuntimeError, match='modified in place'):
+        T.GradNorm(net, w0, *rows)
 
 
 def test_gradnorm_fused_path_at_scale_and_through_rwf_layers():

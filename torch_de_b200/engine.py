@@ -256,13 +256,17 @@ class _JetFunction(torch.autograd.Function):
 
 class JetForwardRecord:
     """Handle on one stash-keeping forward: lets `grad_balance.GradNorm` run range-restricted reverse sweeps on it."""
-    __slots__ = ('runner', 'net', 'x', 'stash', 'params')
+    __slots__ = ('runner', 'net', 'x', 'stash', 'params', 'versions')
 
     def __init__(self, runner, net, x, stash, params):
         self.runner, self.net, self.x, self.stash, self.params = runner, net, x, stash, params
+        self.versions = [p._version for p in params]     # like autograd's saved-tensor check: the stash belongs to THESE weights
 
     def gradient(self, seeds: torch.Tensor, point_range=None, flat_grad: Optional[torch.Tensor] = None) -> torch.Tensor:
         """flat parameter gradient (net.parameters() order of the Linear layers) of sum(seeds * block)."""
+        if any(p._version != v for p, v in zip(self.params, self.versions)):
+            raise RuntimeError("the network parameters were modified in place after this forward (optimizer.step()?): "
+                               "its activation stash no longer matches them")
         if point_range is not None:
             lo, hi = point_range
             if hi <= lo:
