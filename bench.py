@@ -230,7 +230,8 @@ def workload_name(w):
     return {"ldc": "Tutorials/Lid_Driven_Cavity.py: steady 2D Navier-Stokes (u,v,p), MLP 8x256 tanh, 10 derivative names (J=5)",
             "burgers": "Tutorials/Burgers1D.py: MLP 8x64 tanh (J=4)", "allen_cahn": "Tutorials/AllenCahn.py: MLP 6x128 tanh (J=4)",
             "spring": "Tutorials/Spring.py: Sequential(1,200,1) tanh (J=3)",
-            "cylinder": "Tutorials/Stokes_Cylinder.py: steady 2D Navier-Stokes, MLP 10x512 tanh (J=5)"}[w]
+            "cylinder": "Tutorials/Stokes_Cylinder.py: steady 2D Navier-Stokes, MLP 10x512 tanh (J=5)",
+            "cylinder_unsteady": "Tutorials/Unsteady_Cylinder.py: 2D+t Navier-Stokes (x,y,t), MLP 10x512 tanh (J=6)"}[w]
 
 
 # ------------------------------------------------------------------------------------------------
