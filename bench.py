@@ -303,7 +303,16 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     def timed(n_steps, from_host):
+        import gc
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()          # no generation-2 collection of the interpreter (tens of ms) inside a 0.5-1 s timed region
+        try:
+            return _timed(n_steps, from_host, e0, e1)
+        finally:
+            gc.enable()
+
+    def _timed(n_steps, from_host, e0, e1):
         barrier()
         e0.record()
         for _ in range(n_steps):
