@@ -80,7 +80,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.2)          # the recipe's 200 ms (nvidia-smi -lms 200)
 
     def __enter__(self):
         if self.nv is not None:
