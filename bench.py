@@ -427,7 +427,12 @@ def run_ours(args, rank, local_rank, world):
         ms.append(m.value)
         cnt.append(n.value)
     kernels = []
-    fwd_flops = (1.0 / 3.0) * f_pt * pts_total * (2 if recompute else 1)
+    # recompute mode: the backward re-runs the forward chunk by chunk, except for the last chunk whose stash the first pass kept
+    fwd_passes = 1.0
+    if recompute:
+        chunk = max(runner.chunking.values())
+        fwd_passes = 2.0 - 1.0 / max(1, -(-n_pts_rank // chunk))
+    fwd_flops = (1.0 / 3.0) * f_pt * pts_total * fwd_passes
     kernels.append(dict(kernel="jet_forward_tc_kernel" if paths & 1 else "jet_forward_kernel", flops=fwd_flops, ms=ms[0],
                         launches=cnt[0], tensor=bool(paths & 1)))
     if paths & 2:

@@ -69,6 +69,7 @@ class JetRunner:
         self._plans: Dict[int, _lib.TdePlan] = {}
         self._workspace: Optional[torch.Tensor] = None
         self._last_forward = None
+        self._chunk_stash_owner = None
         self._chunk_stash: Optional[torch.Tensor] = None
         self.chunking: Dict[tuple, int] = {}
 
@@ -123,12 +124,19 @@ class JetRunner:
                 raise RuntimeError(f"network parameters live on {p.device} but the input is on {x.device}")
         return x.contiguous()
 
-    def forward(self, x: torch.Tensor, tensors: Sequence[torch.Tensor], need_stash: bool, reuse_stash: bool = False):
+    def forward(self, x: torch.Tensor, tensors: Sequence[torch.Tensor], need_stash: bool, reuse_stash: bool = False,
+                out: Optional[torch.Tensor] = None, out_col: int = 0, owner=None):
         """reuse_stash: keep the stash in a buffer owned by the runner (recompute mode: it only lives until the matching
-        backward of the same chunk, and re-allocating ~100 GB blocks every chunk fragments the caching allocator)."""
+        backward of the same chunk, and re-allocating ~100 GB blocks every chunk fragments the caching allocator); `owner`
+        tags who may still rely on that buffer's contents (`_chunk_stash_owner`).
+        out / out_col: write the streams into columns [out_col, out_col + B) of an existing [rows, B_total] block."""
         x = self._check_x(x)
         B = x.shape[0]
-        out = torch.empty((self.ch.n_rows, B), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((self.ch.n_rows, B), dtype=torch.float32, device=x.device)
+            out_col = 0
+        elif out.dim() != 2 or out.shape[0] != self.ch.n_rows or out_col < 0 or out_col + B > out.shape[1] or not out.is_contiguous():
+            raise ValueError("output block does not hold these columns")
         if B == 0:
             return x, out, None
         plan = self.plan(B)
@@ -139,13 +147,15 @@ class JetRunner:
                 self._chunk_stash = None
                 self._chunk_stash = torch.empty(plan.stash_bytes // 4, dtype=torch.float32, device=x.device)
             stash = self._chunk_stash
+            self._chunk_stash_owner = owner
         elif need_stash:
             stash = torch.empty(plan.stash_bytes // 4, dtype=torch.float32, device=x.device)
         # a forward that keeps no stash (inference, value-only groups, the first pass of recompute mode) only needs the
         # packed weights; the full workspace (gradient slabs, Hbar stream) belongs to a forward/backward pair
         ws = self._ws(plan.workspace_bytes if need_stash else plan.workspace_forward_bytes, x.device)
         with _lib.on_device(x.device):
-            rc = _lib.lib().tde_jet_forward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B, out.data_ptr(), B,
+            rc = _lib.lib().tde_jet_forward(C.byref(self._net), C.byref(self._spec), x.data_ptr(), B,
+                                            out.data_ptr() + 4 * out_col, out.shape[1],
                                             stash.data_ptr() if need_stash else None, ws.data_ptr(), self._stream(x.device))
         _lib.check(rc, "tde_jet_forward")
         return x, out, stash
@@ -224,7 +234,22 @@ class _JetFunction(torch.autograd.Function):
                         n_chunks += 1
                 runner.chunking[key] = chunk
             ctx.chunk = runner.chunking[key]
-        xc, out, stash = runner.forward(x, params, need_stash=need and ctx.chunk == 0)
+        ctx.kept = None
+        if need and ctx.chunk > 0:
+            # recompute mode.  The first pass keeps nothing -- except for the LAST chunk, whose stash goes into the runner's
+            # chunk buffer: the backward starts with that chunk and need not run its forward again (1 / n_chunks of the
+            # recompute).  Another forward through this runner before the backward simply takes the buffer over (owner tag).
+            B = x.shape[0]
+            lo_last = ((B - 1) // ctx.chunk) * ctx.chunk
+            xc = runner._check_x(x)
+            out = torch.empty((runner.ch.n_rows, B), dtype=torch.float32, device=x.device)
+            if lo_last > 0:
+                runner.forward(xc[:lo_last], params, need_stash=False, out=out, out_col=0)
+            ctx.kept = object()
+            runner.forward(xc[lo_last:], params, need_stash=True, reuse_stash=True, out=out, out_col=lo_last, owner=ctx.kept)
+            stash = None
+        else:
+            xc, out, stash = runner.forward(x, params, need_stash=need and ctx.chunk == 0)
         ctx.runner = runner
         ctx.stash = stash
         ctx.need = need
@@ -246,7 +271,11 @@ class _JetFunction(torch.autograd.Function):
         else:   # recompute mode
             flat = torch.zeros(runner.n_params, dtype=torch.float32, device=x.device)
             grad_out = grad_out.contiguous()
-            for lo in range(0, B, ctx.chunk):
+            starts = list(range(0, B, ctx.chunk))
+            if ctx.kept is not None and runner._chunk_stash_owner is ctx.kept:
+                lo = starts.pop()          # the forward left this chunk's stash in the runner's buffer
+                runner.backward(x[lo:B], params, runner._chunk_stash, grad_out[:, lo:B], flat_grad=flat, seeds_ld=B)
+            for lo in starts:
                 hi = min(B, lo + ctx.chunk)
                 xc, _, stash = runner.forward(x[lo:hi], params, need_stash=True, reuse_stash=True)
                 runner.backward(xc, params, stash, grad_out[:, lo:hi], flat_grad=flat, seeds_ld=B)
