@@ -1,14 +1,15 @@
-// tcgen05 reverse sweep for wide layers (W = 128 or 256), two kernels:
+// tcgen05 reverse sweep for wide layers (padded width W = 128, 256 or 512), two kernels:
 //
 //  jet_backward_tc_kernel : seeds -> Hbar jets of every layer.  The dX GEMMs  Zbar_{l-1}[k][col] = sum_n W_l[n][k] Hbar_l[n][col]
 //      run on the tensor cores exactly like the forward (A = W_l^T image streamed + multicast, B = Hbar planes resident in
-//      smem, D in TMEM with lane = neuron, 3xTF32, same issue loop).  The epilogue thread owns one neuron for 8 points of
-//      the tile, so the activation adjoint, the bias gradients, dW_out and dW_in need no cross-thread reduction (the two
-//      threads of a neuron add into two copies of the small slab sections).  It also writes Hbar_l to HBM
+//      smem, D in TMEM with lane = neuron, 3xTF32, same issue loop).  An epilogue thread owns one neuron for 4 (W = 512: 8)
+//      points of the tile, so the activation adjoint, the bias gradients, dW_out and dW_in need no cross-thread reduction (the
+//      threads of a neuron add into separate copies of the small slab sections).  It also writes Hbar_l to HBM
 //      ([layer][tile][column][neuron], coalesced) for the weight-gradient kernel.
 //
 //  jet_dw_tc_kernel       : dW_l[n][k] = sum_{points, channels} Hbar_l[n][col] * Z_{l-1}[k][col]  as a split-K tensor-core GEMM
-//      (M = n, N = k = 256 TMEM columns per neuron block, K = jet columns).  A producer thread streams Hbar_l and the stash
+//      (M = n, N = k = 256 TMEM columns per neuron block, K = jet columns; W = 512 as 2 x 2 quadrants of 256 x 256 spread over
+//      the CTAs).  A producer thread streams Hbar_l and the stash
 //      of layer l-1 with cp.async.bulk into raw stages; splitter threads turn the stash into Z on the fly, split both
 //      3xTF32 and lay them out as K-major UMMA core matrices; the accumulator is flushed to the CTA's private gradient
 //      slab every few tiles (FP32 RED, single writer) so the tensor core's round-toward-zero accumulation never runs long

@@ -1,7 +1,7 @@
-// tcgen05 forward for wide layers (W = 128 or 256): hidden-layer GEMMs on the 5th-gen tensor cores with a
+// tcgen05 forward for wide layers (padded width W = 128, 256 or 512): hidden-layer GEMMs on the 5th-gen tensor cores with a
 // 3xTF32 split (hi*hi + hi*lo + lo*hi, FP32 accumulate in TMEM) to hold FP32 accuracy.
 //
-//   D[neuron][col] = sum_k W_l[neuron][k] * Z[k][col]        col = pt*J + channel, 16 points per CTA tile
+//   D[neuron][col] = sum_k W_l[neuron][k] * Z[k][col]        col = pt*J + channel, 16 points per CTA tile (W = 512: 8 or 4)
 //
 // A operand = weights (M = 128 neurons per block, K-major): streamed by a producer thread with cp.async.bulk (multicast to
 //             the cluster peer) from a global image that is already in UMMA core-matrix order and already split into hi/lo.
@@ -9,8 +9,9 @@
 //             side by side per k-atom (see TcPlanes / tc_issue_layer), written by the epilogue of the previous layer.
 // D         = TMEM, lane = neuron => after tcgen05.ld every epilogue thread owns ALL jet channels of its neuron for its
 //             points of the tile, which is exactly what the jet activation needs (no cross-lane exchange).
-// Roles: warp 0 weight producer, warp 1 MMA issuer (one elected thread), warps 4.. epilogue (8 warps per 128-neuron block:
-// one thread per neuron and half of the tile's points).  Shared memory: [planes][weight stages][x][y][barriers].
+// Roles: warp 0 weight producer, warp 1 MMA issuer (one elected thread), warps 4..19 epilogue (W <= 256: every warp serves
+// the neuron blocks in turn, one thread per neuron and 4 points; W = 512: one warp per block and TMEM lane quarter).
+// Shared memory: [planes][weight stages][x][y][barriers]; w_out is read through L1.
 #pragma once
 #include <type_traits>
 #include <utility>
